@@ -1,0 +1,181 @@
+/*
+ * xnart.h — C ABI of libxnart.so, the B200-native per-pixel trace loop that replaces the
+ * worker fan-out of RayTracer.RenderInternal (RayTraceProject/RayTraceProject/RayTracer.cs:103-126).
+ *
+ * The reference has no FFI seam on this path (its only DllImports are avifil32/winmm,
+ * aviFileWrapper_src/Avi.cs:175-377), so this boundary is new; every entry point cites the
+ * reference interface whose work it takes over.  All structs are plain-old-data with natural
+ * alignment (no padding surprises: only 4-byte scalars and one pointer at the end of
+ * XnartMaterial), all functions are extern "C", take plain pointers and sizes, and return an
+ * int32 status (XNART_OK == 0).  Matrices are XNA row-major, row-vector convention
+ * (M11..M44 in memory order, translation in M41..M43).
+ *
+ * Ownership: input pointers are borrowed for the duration of the call and copied; output
+ * buffers are caller-allocated; the context owns all device memory.
+ * Threading: a context may be used from any thread; calls that touch the device are
+ * serialised per context, a render issued while another is in flight returns XNART_ERR_BUSY
+ * (RayTracer.cs:26-27,62-63 throws InvalidOperationException); xnart_progress may be called
+ * concurrently (Game1.cs:337 polls RayTracer.Progress from the game thread).
+ */
+#ifndef XNART_H
+#define XNART_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------- */
+enum {
+    XNART_OK = 0,
+    XNART_ERR_INVALID_ARGUMENT = 1, /* bad enum / null pointer -> ArgumentException (Material.cs:85,97) */
+    XNART_ERR_BUSY = 2,             /* render in flight -> InvalidOperationException (RayTracer.cs:62-63) */
+    XNART_ERR_CUDA = 3,             /* any CUDA runtime failure; text in xnart_last_error */
+    XNART_ERR_NOT_BUILT = 4,        /* render/trace before xnart_build_scene */
+    XNART_ERR_OCTREE_DEPTH = 5,     /* MeshOctree.BuildTree (MeshOctree.cs:84-96) would recurse without bound */
+    XNART_ERR_NO_DEVICE = 6,        /* no usable CUDA device: there is no CPU fallback */
+    XNART_ERR_OUT_OF_MEMORY = 7,
+    XNART_ERR_UNSUPPORTED = 8
+};
+
+/* ---- enums mirrored from the reference ------------------------------------------------ */
+enum { XNART_FILTER_POINT = 0, XNART_FILTER_BILINEAR = 1 };                /* Material.cs:12-16 TextureFiltering */
+enum { XNART_ADDRESS_CLAMP = 0, XNART_ADDRESS_WRAP = 1, XNART_ADDRESS_MIRROR = 2 }; /* Material.cs:18-23 UVAddressMode */
+enum { XNART_LIGHT_SPOT = 0, XNART_LIGHT_DIRECTIONAL = 1 };                /* SpotLight.cs / DirectionalLight.cs */
+/* Semantics of the closed-source framework calls on the path:
+ * XNA40 = Microsoft.Xna.Framework 4.0 (canonical; what the reference links,
+ * RayTraceProject.csproj:65); MONOGAME = MonoGame's re-implementation. */
+enum { XNART_SEMANTICS_XNA40 = 0, XNART_SEMANTICS_MONOGAME = 1 };
+
+/* ---- scene records -------------------------------------------------------------------- */
+/* Triangle.cs:14-25 (managed class, flattened by the shim at Mesh.Init time). */
+typedef struct XnartTriangle {
+    float v1[3], v2[3], v3[3];
+    float uv1[2], uv2[2], uv3[2];
+    float n1[3], n2[3], n3[3];
+    float surfaceNormal[3];
+    float color[4];
+    int32_t id;
+} XnartTriangle; /* 32 x 4 = 128 bytes */
+
+/* Material.cs:28-39 + RayTracerTexture.cs:12-18 (ColorData: 0xAARRGGBB, top-down rows). */
+typedef struct XnartMaterial {
+    float reflectiveness;
+    int32_t useTexture, interpolateNormals, transparent;
+    float refractionIndex;
+    int32_t texW, texH;
+    int32_t _pad;
+    const uint32_t* argb; /* texW*texH texels, borrowed; may be NULL when !useTexture */
+} XnartMaterial;
+
+/* SpotLight.cs:12-27, DirectionalLight.cs:11-14. */
+typedef struct XnartLight {
+    int32_t kind;
+    float position[3], direction[3], color[3];
+    float intensity, decayExponent, spotAngle;
+} XnartLight;
+
+/* RayTracer.cs:19-41 (properties) + :395-397 (view/proj/viewport captured per render). */
+typedef struct XnartFrame {
+    float view[16], proj[16];
+    int32_t vpX, vpY, vpW, vpH;
+    float minDepth, maxDepth;
+    int32_t maxReflections; /* RayTracer.MaxReflections, RayTracer.cs:33 */
+    int32_t filtering;      /* XNART_FILTER_*  */
+    int32_t addressMode;    /* XNART_ADDRESS_* */
+    int32_t semantics;      /* XNART_SEMANTICS_* (colour pack + slab test form) */
+    /* Row sharding for multi-GPU (RayTracer.cs:49-52 treats scanlines as independent work
+     * items): this call renders only scanline bands b with (b % shardCount) == shardIndex,
+     * a band being shardBandRows consecutive scanlines.  shardCount <= 1 renders everything. */
+    int32_t shardIndex, shardCount, shardBandRows;
+    int32_t _pad;
+} XnartFrame;
+
+/* Per-render statistics.  A "ray" is one call of the top-level GetRayIntersection
+ * (RayTracer.cs:485,512).  Box/triangle counters are only filled when counting is enabled
+ * (xnart_set_option(ctx, XNART_OPT_COUNTERS, 1)); ray counts are always filled. */
+typedef struct XnartCounters {
+    uint64_t raysPrimary, raysShadow, raysReflection, raysRefraction;
+    uint64_t hits;        /* closest-hit queries that returned a hit (shaded fragments) */
+    uint64_t nBox;        /* slab tests executed (mesh-level + scene-level + Mesh.RayIntersects) */
+    uint64_t nTriRef;     /* leaf triangle references fetched */
+    uint64_t nTriCulled;  /* triangle tests ended by the backface cull (RayExtensions.cs:50-51) */
+    uint64_t nTriFull;    /* triangle tests run to the end */
+    uint64_t pixels;
+    double msTotal;       /* device time of the last render (CUDA events) */
+    double msLevels;      /* ... of the trace+shade kernels */
+    double msResolve;     /* ... of the bottom-up colour resolve */
+    double msCopy;        /* ... of the device->host copy */
+} XnartCounters;
+
+enum {
+    XNART_OPT_COUNTERS = 1,      /* 0/1: run the instrumented kernels (slower) */
+    XNART_OPT_ARENA_BYTES = 2,   /* upper bound for the per-render path arena (default 8 GiB) */
+    XNART_OPT_SEMANTICS = 3      /* default semantics for xnart_trace_rays */
+};
+
+typedef struct XnartCtx XnartCtx;
+
+/* Context on one or more devices of this process (scene replicated on each).
+ * Replaces: new RayTracer() (Game1.cs:119). */
+int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds);
+int32_t xnart_destroy(XnartCtx* ctx);
+const char* xnart_last_error(XnartCtx* ctx); /* ctx may be NULL (create failures) */
+int32_t xnart_set_option(XnartCtx* ctx, int32_t option, int64_t value);
+
+/* Mesh.Init() (Mesh.cs:27-32): builds the per-mesh octree natively, restating
+ * MeshOctree.Build/BuildTree/SplitCuboid (MeshOctree.cs:56-96,204-236).  meshBoxMinMax is
+ * Mesh.MeshBoundingBox (min xyz, max xyz); itemThreshold is MeshOctree.itemTreshold (50). */
+int32_t xnart_add_mesh(XnartCtx* ctx, const XnartTriangle* tris, int64_t nTri,
+                       const XnartMaterial* material, const float meshBoxMinMax[6],
+                       int32_t itemThreshold, int32_t* meshIdOut);
+
+/* new SceneObject + scene.Bodies.Add (Game1.cs:102-105): an instance of one or more meshes
+ * with SceneObject.World / InverseWorld (SceneObject.cs:187-198) and the object's local
+ * BoundingBox (SceneObject.cs:131). */
+int32_t xnart_add_object(XnartCtx* ctx, const int32_t* meshIds, int32_t nMesh,
+                         const float world[16], const float inverseWorld[16],
+                         const float localBoxMinMax[6], int32_t* objIdOut);
+
+/* OctreeSpatialManager.Build (OctreeSpatialManager.cs:64-99); itemThreshold = 20.  Flattens
+ * and uploads the scene to every device of the context. */
+int32_t xnart_build_scene(XnartCtx* ctx, int32_t itemThreshold);
+
+/* RayTracer.Lights (RayTracer.cs:36-39). */
+int32_t xnart_set_lights(XnartCtx* ctx, const XnartLight* lights, int32_t n);
+
+/* The body of RayTracer.RenderInternal (RayTracer.cs:103-126): fills renderTargetData
+ * (vpW*vpH packed R | G<<8 | B<<16 | A<<24, row-major top-down) in host memory. */
+int32_t xnart_render_frame(XnartCtx* ctx, const XnartFrame* frame, uint32_t* rgba8Out);
+
+/* Same, but the output stays on the context's first device: devRgba8Out is a device pointer
+ * to vpW*vpH uint32 and the work is enqueued on cudaStream (a cudaStream_t passed as void*,
+ * NULL = the context's own stream, in which case the call returns after completion). */
+int32_t xnart_render_frame_device(XnartCtx* ctx, const XnartFrame* frame,
+                                  void* devRgba8Out, void* cudaStream);
+
+/* Batch form of ISpatialManager.GetRayIntersection (ISpatialManager.cs:15;
+ * OctreeSpatialManager.cs:312-455) for parity testing: rays6 = n x (position xyz, direction
+ * xyz); ignoreMeshTri2 = n x (meshId, triangleId) or NULL (-1,-1 = nothing ignored).
+ * Misses report objId = meshId = triId = -1. worldPos3 may be NULL. */
+int32_t xnart_trace_rays(XnartCtx* ctx, const float* rays6, int64_t n,
+                         const int32_t* ignoreMeshTri2,
+                         int32_t* objId, int32_t* meshId, int32_t* triId,
+                         float* u, float* v, float* d, float* worldPos3);
+
+int32_t xnart_get_counters(XnartCtx* ctx, XnartCounters* out);
+
+/* RayTracer.Progress (RayTracer.cs:43-46): fraction of the current render that is done. */
+float xnart_progress(XnartCtx* ctx);
+
+/* Number of CUDA kernels launched by this context so far (for bench.py's gpu_launches). */
+int64_t xnart_kernel_launches(XnartCtx* ctx);
+
+/* Version / build string (arch, flags). */
+const char* xnart_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XNART_H */
