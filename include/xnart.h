@@ -175,6 +175,22 @@ int64_t xnart_kernel_launches(XnartCtx* ctx);
 /* Version / build string (arch, flags). */
 const char* xnart_version(void);
 
+/* Page-locked host memory for renderTargetData (RayTracer.cs:16, the Color[] the render fills):
+ * a frame buffer allocated here receives the device->host copy directly, without staging. */
+void* xnart_alloc_host(int64_t bytes);
+void xnart_free_host(void* p);
+
+/* Structural export of the flattened octrees, for tests (host data only; also available in a
+ * host-only context created with nDevices == 0).  which: 0 = MeshOctree of mesh `id`
+ * (MeshOctree.cs:56-96), 1 = the scene octree (OctreeSpatialManager.cs:64-113).  Nodes are in
+ * breadth order, the 8 children of a node consecutive; leaf: w0 = first reference, w1 = count;
+ * internal: w0 = first child, w1 = -1 - index into consMax3; refs = leaf lists in depth-first
+ * leaf order. */
+int32_t xnart_debug_tree_info(XnartCtx* ctx, int32_t which, int32_t id, int32_t* nNodes,
+                              int32_t* nRefs, int32_t* nCons, int32_t* depth);
+int32_t xnart_debug_tree_dump(XnartCtx* ctx, int32_t which, int32_t id, float* lo3, float* hi3,
+                              int32_t* w0, int32_t* w1, float* consMax3, int32_t* refs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,216 @@
+"""ctypes binding of libxnart.so (include/xnart.h).
+
+This is the same ABI a C# P/Invoke shim binds.  There is no CPU fallback: if the
+library has not been built the import of the *library* (not of this module) raises, and every
+compute call on a box without a CUDA device raises `XnartError(XNART_ERR_NO_DEVICE)`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .records import (TRIANGLE_DTYPE, XNART_ERR_BUSY, XNART_ERR_INVALID_ARGUMENT, XnartCounters, XnartFrame,
+                      f32_array, make_light_array, make_material)
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libxnart.so")
+_lib = None
+
+
+class XnartError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("xnart error %d: %s" % (code, msg))
+        self.code = code
+
+
+class BusyError(XnartError):
+    """RayTracer.RenderAsync throws InvalidOperationException while IsBusy (RayTracer.cs:62-63)."""
+
+
+def build(force=False, verbose=False):
+    """Compile libxnart.so in-tree with nvcc for sm_100a (csrc/Makefile)."""
+    cmd = ["make", "-C", os.path.join(_PKG, "csrc")] + (["-B"] if force else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libxnart.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load libxnart.so; raises if it is missing (the product path never falls back to the CPU)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.xnart_last_error.restype = C.c_char_p
+        L.xnart_last_error.argtypes = [C.c_void_p]
+        L.xnart_version.restype = C.c_char_p
+        L.xnart_progress.restype = C.c_float
+        L.xnart_progress.argtypes = [C.c_void_p]
+        L.xnart_kernel_launches.restype = C.c_int64
+        L.xnart_kernel_launches.argtypes = [C.c_void_p]
+        L.xnart_alloc_host.restype = C.c_void_p
+        L.xnart_alloc_host.argtypes = [C.c_int64]
+        L.xnart_free_host.argtypes = [C.c_void_p]
+        L.xnart_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
+        L.xnart_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.xnart_render_frame_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+EXPORTS = [
+    "xnart_create", "xnart_destroy", "xnart_last_error", "xnart_set_option", "xnart_add_mesh", "xnart_add_object",
+    "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_trace_rays",
+    "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
+    "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump",
+]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedFrame:
+    """A (H, W) uint32 frame in page-locked memory (xnart_alloc_host)."""
+
+    def __init__(self, height, width):
+        self._l = lib()
+        self.nbytes = height * width * 4
+        self.ptr = self._l.xnart_alloc_host(self.nbytes)
+        if not self.ptr:
+            raise XnartError(7, "xnart_alloc_host failed")
+        buf = (C.c_uint32 * (height * width)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.uint32).reshape(height, width)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._l.xnart_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Xnart:
+    """One libxnart context (`new RayTracer()` + scene, Game1.cs:98-138)."""
+
+    def __init__(self, devices=(0,)):
+        self._l = lib()
+        self._h = C.c_void_p()
+        n = len(devices)
+        ids = (C.c_int32 * max(1, n))(*devices)
+        rc = self._l.xnart_create(C.byref(self._h), C.c_int32(n), ids)
+        if rc != 0:
+            raise XnartError(rc, self._l.xnart_last_error(None).decode())
+        self.n_devices = n
+
+    def close(self):
+        if self._h:
+            self._l.xnart_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            if rc == XNART_ERR_BUSY:
+                raise BusyError(rc, self._l.xnart_last_error(None).decode())
+            raise XnartError(rc, self._l.xnart_last_error(self._h).decode())
+
+    def set_option(self, option, value):
+        self._check(self._l.xnart_set_option(self._h, C.c_int32(option), C.c_int64(value)))
+
+    def add_mesh(self, tris, reflectiveness=0.0, use_texture=False, interpolate_normals=False, transparent=False,
+                 refraction_index=0.0, argb=None, box=None, item_threshold=50):
+        tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DTYPE)
+        mat, _keep = make_material(reflectiveness, use_texture, interpolate_normals, transparent, refraction_index, argb)
+        out = C.c_int32(-1)
+        self._check(self._l.xnart_add_mesh(self._h, _p(tris), C.c_int64(len(tris)), C.byref(mat), f32_array(box, 6),
+                                           C.c_int32(item_threshold), C.byref(out)))
+        return out.value
+
+    def add_object(self, mesh_ids, world, inverse_world, local_box):
+        ids = (C.c_int32 * max(1, len(mesh_ids)))(*mesh_ids)
+        out = C.c_int32(-1)
+        self._check(self._l.xnart_add_object(self._h, ids, C.c_int32(len(mesh_ids)), f32_array(world, 16),
+                                             f32_array(inverse_world, 16), f32_array(local_box, 6), C.byref(out)))
+        return out.value
+
+    def build_scene(self, item_threshold=20):
+        self._check(self._l.xnart_build_scene(self._h, C.c_int32(item_threshold)))
+
+    def set_lights(self, lights):
+        arr = make_light_array(lights)
+        self._check(self._l.xnart_set_lights(self._h, arr, C.c_int32(len(lights))))
+
+    def render_frame(self, frame, out=None):
+        """xnart_render_frame: host buffer in, host buffer out (copies inside the call)."""
+        if out is None:
+            out = np.zeros((frame.vpH, frame.vpW), dtype=np.uint32)
+        arr = out.array if isinstance(out, PinnedFrame) else out
+        assert arr.dtype == np.uint32 and arr.size == frame.vpH * frame.vpW and arr.flags["C_CONTIGUOUS"]
+        self._check(self._l.xnart_render_frame(self._h, C.addressof(frame), arr.ctypes.data))
+        return arr
+
+    def render_frame_device(self, frame, dev_ptr, stream=None):
+        """xnart_render_frame_device: output stays in device memory at `dev_ptr` (e.g. a torch tensor's data_ptr())."""
+        self._check(self._l.xnart_render_frame_device(self._h, C.addressof(frame), C.c_void_p(dev_ptr),
+                                                      C.c_void_p(stream) if stream else None))
+
+    def trace_rays(self, rays6, ignore=None):
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float32).reshape(-1, 6)
+        n = len(rays6)
+        ign = None if ignore is None else np.ascontiguousarray(ignore, dtype=np.int32).reshape(-1, 2)
+        res = dict(obj=np.zeros(n, np.int32), mesh=np.zeros(n, np.int32), tri=np.zeros(n, np.int32),
+                   u=np.zeros(n, np.float32), v=np.zeros(n, np.float32), d=np.zeros(n, np.float32),
+                   pos=np.zeros((n, 3), np.float32))
+        self._check(self._l.xnart_trace_rays(self._h, _p(rays6), C.c_int64(n), _p(ign) if ign is not None else None,
+                                             _p(res["obj"]), _p(res["mesh"]), _p(res["tri"]), _p(res["u"]),
+                                             _p(res["v"]), _p(res["d"]), _p(res["pos"])))
+        return res
+
+    def counters(self):
+        c = XnartCounters()
+        self._check(self._l.xnart_get_counters(self._h, C.byref(c)))
+        return c
+
+    def progress(self):
+        return float(self._l.xnart_progress(self._h))
+
+    def kernel_launches(self):
+        return int(self._l.xnart_kernel_launches(self._h))
+
+    def tree(self, mesh_id=None):
+        """Flattened octree (breadth order) of a mesh, or of the scene when mesh_id is None."""
+        which, mid = (1, 0) if mesh_id is None else (0, mesh_id)
+        nn, nr, nc, dp = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._l.xnart_debug_tree_info(self._h, which, mid, C.byref(nn), C.byref(nr), C.byref(nc), C.byref(dp)))
+        n = nn.value
+        out = dict(lo=np.zeros((n, 3), np.float32), hi=np.zeros((n, 3), np.float32), w0=np.zeros(n, np.int32),
+                   w1=np.zeros(n, np.int32), cons_max=np.zeros((max(1, nc.value), 3), np.float32),
+                   refs=np.zeros(max(1, nr.value), np.int32), depth=dp.value)
+        self._check(self._l.xnart_debug_tree_dump(self._h, which, mid, _p(out["lo"]), _p(out["hi"]), _p(out["w0"]),
+                                                  _p(out["w1"]), _p(out["cons_max"]), _p(out["refs"])))
+        out["refs"] = out["refs"][: nr.value]
+        out["cons_max"] = out["cons_max"][: nc.value]
+        return out
+
+
+def version():
+    return lib().xnart_version().decode()

@@ -1,0 +1,123 @@
+// device_types.h — HBM layout of an uploaded scene and of the per-render path arena.
+//
+// Octree nodes (MeshOctree.CubeNode, MeshOctree.cs:32-40; OctreeSpatialManager.CubeNode,
+// OctreeSpatialManager.cs:37-48) of every mesh tree and of the scene tree live in ONE array in
+// breadth order per tree; the 8 children of a node are consecutive (child c = 4i+2j+k,
+// MeshOctree.cs:210-222), so one child block is 8 x 32 B = 256 contiguous bytes.
+//
+//   node n = { float4 lo = (Min.xyz, w0), float4 hi = (Max.xyz, w1) }
+//     leaf     : w0 = first position in refs[] (global), w1 = item count (>= 0)
+//     internal : w0 = global index of child 0,           w1 = -1 - consIndex (< 0)
+//   consMax[consIndex] = component-wise max of Max over the node and all its descendants
+//   (a child's Max = (Min + size*i) + size can overshoot its parent's Max by rounding,
+//   MeshOctree.cs:217-218; pruning must use the conservative box, descending the node's own).
+//
+//   refs[] : leaf item lists concatenated in DEPTH-FIRST leaf order (children 0..7), so the
+//            position of an item in refs[] reproduces the reference's visiting order inside a
+//            group of equal-key leaves (MeshOctree.cs:283-288): ties in distance resolve to the
+//            smallest position.  Mesh trees store mesh-relative triangle indices, the scene tree
+//            stores object ids.
+//
+// Triangles (Triangle.cs:14-25) are split into a 64-byte intersection record and an 80-byte
+// shading record, both arrays of float4 read with 128-bit loads:
+//   triI[4t+0] = (n.xyz, 0)  triI[4t+1] = (v1.xyz, 0)  triI[4t+2] = (E1.xyz, 0)  triI[4t+3] = (E2.xyz, 0)
+//       n = surfaceNormal comes first so a triangle rejected by the backface test
+//       (RayExtensions.cs:49-51) costs one 32-byte sector; a 64-byte aligned record never
+//       straddles more than two sectors.  E1 = v2 - v1, E2 = v3 - v1 are computed once on the
+//       host in binary32 — bit-identical to the per-test recomputation at RayExtensions.cs:54-55.
+//   triS[5t+0] = (uv1.xy, uv2.xy) triS[5t+1] = (uv3.xy, n1.xy) triS[5t+2] = (n1.z, n2.xyz)
+//   triS[5t+3] = (n3.xyz, color.x) triS[5t+4] = (color.yzw, 0)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace xn {
+
+constexpr int kMaxLights = 16;
+constexpr int kMeshStack = 160;   // >= 7*depth+1 -> mesh octree depth <= 22
+constexpr int kSceneStack = 64;   // scene octree depth <= 9
+constexpr int kMaxMeshDepth = (kMeshStack - 1) / 7;
+constexpr int kMaxSceneDepth = (kSceneStack - 1) / 7;
+constexpr int kBuilderDepthGuard = 64;  // same guard as the oracle: deeper -> XNART_ERR_OCTREE_DEPTH
+
+struct DevMesh {
+    float box[6];        // Mesh.MeshBoundingBox (Mesh.cs:34-39 prefilter)
+    int rootNode;        // global node index of the MeshOctree root
+    int triBase;         // first triangle of this mesh in triI/triS
+    float reflectiveness;
+    float oneMinusReflectiveness;  // 1.0f - Reflectiveness (RayTracer.cs:584), hoisted
+    float refractionIndex;
+    int flags;           // bit0 useTexture, bit1 interpolateNormals, bit2 transparent
+    int texOffset;       // first texel in texels[]
+    int texW, texH;
+    int _pad;
+};
+enum { MESH_USE_TEXTURE = 1, MESH_INTERP_NORMALS = 2, MESH_TRANSPARENT = 4 };
+
+struct DevObj {
+    float world[16];     // SceneObject.World (row-major; column 4 unused by Vector3.Transform)
+    float inv[16];       // SceneObject.InverseWorld
+    int meshStart, meshCount;  // range in objMeshIds[]
+    int _pad[2];
+};
+
+struct DevLight {
+    int kind;
+    float px, py, pz, dx, dy, dz, cr, cg, cb;
+    float intensity;
+    float angleCosine;   // (float)Math.Cos(spotAngle * 0.5f), SpotLight.cs:25
+    double powDen;       // Math.Pow(1 - angleCosine, DecayExponent), SpotLight.cs:54 (ray independent)
+};
+
+struct DevScene {
+    const float4* nodes;
+    const float4* consMax;
+    const int* refs;
+    const float4* triI;
+    const float4* triS;
+    const DevMesh* meshes;
+    const DevObj* objs;
+    const int* objMeshIds;
+    const uint32_t* texels;
+    int sceneRoot;
+    int nMeshes, nObjs;
+};
+
+struct DevFrame {
+    float inv[16];       // Invert(Identity * view * proj), computed once per frame on the host
+    int vpX, vpY, vpW, vpH;
+    float minDepth, maxDepth;
+    int maxReflections, filtering, addressMode, semantics;
+    int shardIndex, shardCount, shardBandRows;
+    int nLights;
+    // chunk of shard-local pixels handled by this launch sequence
+    long long pixelBase;   // first shard-local pixel index of the chunk
+    int chunkPixels;
+    int _pad;
+};
+
+// Per-render path arena (SoA over "path nodes": one node per traced primary/reflection/refraction ray).
+struct DevArena {
+    float4* nodeA;       // (lightResult.xyz, 1 - Reflectiveness)
+    float4* nodeB;       // (surfaceColor.xyz, triangle.color.W)
+    uint2* nodeC;        // (reflection child node, refraction child node or 0xFFFFFFFF)
+    uint32_t* color;     // resolved RGBA8 of the node (Color struct, RayTracer.cs:705,726,732)
+    uint32_t* flags;     // 0 = colour final, 1 = needs resolve
+    // ray queues (ping-pong): rays of level L are read, rays of level L+1 appended
+    float4* rayO[2];     // (origin.xyz, currentRefIndex)
+    float4* rayD[2];     // (direction.xyz, unused)
+    int2* rayIgn[2];     // origin triangle identity (mesh id, triangle index), Q6
+    // level bookkeeping, all device resident so a frame needs no host round trip
+    unsigned int* levelCount;   // [maxLevels+2] rays queued per level
+    unsigned int* levelBase;    // [maxLevels+2] first node index of a level
+    unsigned long long* counters;  // kCounterSlots
+    unsigned int nodeCapacity, rayCapacity;
+    unsigned int* overflow;
+};
+
+enum {
+    CTR_RAYS_PRIMARY = 0, CTR_RAYS_SHADOW, CTR_RAYS_REFLECTION, CTR_RAYS_REFRACTION, CTR_HITS,
+    CTR_NBOX, CTR_NTRIREF, CTR_NTRICULLED, CTR_NTRIFULL, CTR_PIXELS, kCounterSlots = 16
+};
+
+}  // namespace xn

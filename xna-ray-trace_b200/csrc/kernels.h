@@ -1,0 +1,24 @@
+// kernels.h — launch wrappers of the trace kernels (implemented in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/xnart.h"
+#include "device_types.h"
+
+namespace xn {
+
+// One wave of the trace loop: closest hit + shadow rays + shading for every ray of `level`.
+// upperBound only sizes the grid (the real count is read on the device).
+cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
+                        long long upperBound, int maxBlocks, bool count, cudaStream_t st);
+
+// Bottom-up colour resolve of one level; level 0 writes the frame.
+cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long long upperBound, int maxBlocks,
+                          uint32_t* out, cudaStream_t st);
+
+// Batch closest-hit queries (xnart_trace_rays).
+cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
+                            int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
+                            int maxBlocks, bool count, cudaStream_t st);
+
+}  // namespace xn

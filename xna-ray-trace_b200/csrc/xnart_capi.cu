@@ -1,0 +1,703 @@
+// xnart_capi.cu — the C ABI of include/xnart.h: context, scene upload, frame rendering.
+//
+// Replaces the worker fan-out of RayTracer.RenderInternal (RayTracer.cs:103-126) with one call.
+// There is NO CPU fallback: every compute entry point needs a CUDA device and fails with
+// XNART_ERR_NO_DEVICE / XNART_ERR_CUDA otherwise.  A context created with nDevices == 0 is
+// "host only": it can build and export the flattened octrees (for structural tests) and nothing else.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xnart.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "scene_build.h"
+#include "xna_math.cuh"
+
+using namespace xn;
+
+namespace {
+
+struct DeviceState {
+    int dev = -1;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    // scene
+    float4* nodes = nullptr; float4* consMax = nullptr; int* refs = nullptr;
+    float4* triI = nullptr; float4* triS = nullptr;
+    DevMesh* meshes = nullptr; DevObj* objs = nullptr; int* objMeshIds = nullptr; uint32_t* texels = nullptr;
+    DevLight* lights = nullptr; int nLightsUploaded = -1;
+    DevScene scene{};
+    // arena
+    DevArena arena{};
+    void* arenaBlock = nullptr; size_t arenaBytes = 0;
+    unsigned arenaNodes = 0, arenaRays = 0;
+    unsigned* levelWords = nullptr;  // levelCount | levelBase | overflow
+    unsigned long long* counters = nullptr;
+    // output
+    uint32_t* frameBuf = nullptr; size_t frameBufPixels = 0;
+    uint32_t* pinned = nullptr; size_t pinnedPixels = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, levels done, resolve done, copy done
+    cudaStream_t lastStream = nullptr;
+    bool countersPending = false;
+    long long lastPixels = 0;
+    int lastLights = 0;
+};
+
+constexpr int kMaxLevels = 30;
+
+inline float __int_as_float_host(int v) {
+    float f;
+    std::memcpy(&f, &v, 4);
+    return f;
+}
+
+}  // namespace
+
+struct XnartCtx {
+    std::vector<DeviceState> devs;
+    std::vector<HostMesh> meshes;
+    std::vector<HostObj> objs;
+    FlatTree sceneTree;
+    std::vector<XnartLight> lights;
+    bool built = false;
+    bool lightsDirty = true;
+    bool hasTransparent = false;
+    std::mutex renderMutex;
+    std::atomic<float> progress{0.0f};
+    std::string err;
+    bool countKernels = false;
+    int64_t arenaLimit = (int64_t)8 << 30;
+    int traceSemantics = XNART_SEMANTICS_XNA40;
+    std::atomic<int64_t> launches{0};
+    XnartCounters last{};
+};
+
+static thread_local std::string g_createError;
+
+static int fail(XnartCtx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_createError = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            char _b[512];                                                                                  \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return fail(ctx, _e == cudaErrorMemoryAllocation ? XNART_ERR_OUT_OF_MEMORY : XNART_ERR_CUDA, _b); \
+        }                                                                                                  \
+    } while (0)
+
+static void freeScene(DeviceState& d) {
+    cudaSetDevice(d.dev);
+    cudaFree(d.nodes); cudaFree(d.consMax); cudaFree(d.refs); cudaFree(d.triI); cudaFree(d.triS);
+    cudaFree(d.meshes); cudaFree(d.objs); cudaFree(d.objMeshIds); cudaFree(d.texels);
+    d.nodes = d.consMax = d.triI = d.triS = nullptr; d.refs = nullptr; d.meshes = nullptr; d.objs = nullptr;
+    d.objMeshIds = nullptr; d.texels = nullptr;
+}
+
+template <class T>
+static cudaError_t uploadVec(T** dst, const std::vector<T>& v) {
+    *dst = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+extern "C" {
+
+const char* xnart_version(void) { return "libxnart 0.1 (sm_100a, -fmad=false, XNA 4.0 semantics)"; }
+
+const char* xnart_last_error(XnartCtx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds) {
+    if (!out || nDevices < 0) return fail(nullptr, XNART_ERR_INVALID_ARGUMENT, "xnart_create: bad arguments");
+    *out = nullptr;
+    XnartCtx* c = new XnartCtx();
+    if (nDevices > 0) {
+        int avail = 0;
+        cudaError_t e = cudaGetDeviceCount(&avail);
+        if (e != cudaSuccess || avail <= 0) {
+            delete c;
+            return fail(nullptr, XNART_ERR_NO_DEVICE,
+                        std::string("no usable CUDA device (") + cudaGetErrorString(e) + "): libxnart has no CPU fallback");
+        }
+        for (int i = 0; i < nDevices; i++) {
+            int id = deviceIds ? deviceIds[i] : i;
+            if (id < 0 || id >= avail) { delete c; return fail(nullptr, XNART_ERR_INVALID_ARGUMENT, "xnart_create: device id out of range"); }
+            DeviceState d;
+            d.dev = id;
+            if (cudaSetDevice(id) != cudaSuccess || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+                delete c;
+                return fail(nullptr, XNART_ERR_CUDA, "xnart_create: cannot initialise device");
+            }
+            cudaDeviceGetAttribute(&d.smCount, cudaDevAttrMultiProcessorCount, id);
+            for (auto& ev : d.ev) cudaEventCreate(&ev);
+            cudaMalloc(&d.levelWords, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2));
+            cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounterSlots);
+            cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounterSlots);
+            c->devs.push_back(d);
+        }
+    }
+    *out = c;
+    return XNART_OK;
+}
+
+int32_t xnart_destroy(XnartCtx* c) {
+    if (!c) return XNART_OK;
+    for (auto& d : c->devs) {
+        cudaSetDevice(d.dev);
+        cudaStreamSynchronize(d.stream);
+        freeScene(d);
+        cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.levelWords); cudaFree(d.counters); cudaFree(d.frameBuf);
+        if (d.pinned) cudaFreeHost(d.pinned);
+        for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(d.stream);
+    }
+    delete c;
+    return XNART_OK;
+}
+
+int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
+    if (!c) return XNART_ERR_INVALID_ARGUMENT;
+    switch (option) {
+        case XNART_OPT_COUNTERS: c->countKernels = value != 0; return XNART_OK;
+        case XNART_OPT_ARENA_BYTES:
+            if (value < (1 << 20)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "arena limit too small");
+            c->arenaLimit = value; return XNART_OK;
+        case XNART_OPT_SEMANTICS:
+            if (value != XNART_SEMANTICS_XNA40) return fail(c, XNART_ERR_UNSUPPORTED, "only XNA 4.0 slab semantics are implemented on the device");
+            c->traceSemantics = (int)value; return XNART_OK;
+        default: return fail(c, XNART_ERR_INVALID_ARGUMENT, "unknown option");
+    }
+}
+
+int32_t xnart_add_mesh(XnartCtx* c, const XnartTriangle* tris, int64_t nTri, const XnartMaterial* material,
+                       const float box[6], int32_t itemThreshold, int32_t* meshIdOut) {
+    if (!c || (!tris && nTri > 0) || nTri < 0 || !material || !box || !meshIdOut || itemThreshold < 0)
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_mesh: bad arguments");
+    if (nTri > 0x7fffffffLL / 8) return fail(c, XNART_ERR_UNSUPPORTED, "xnart_add_mesh: too many triangles");
+    if (material->useTexture && (!material->argb || material->texW <= 0 || material->texH <= 0))
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_mesh: useTexture without texels");
+    std::lock_guard<std::mutex> lk(c->renderMutex);
+    HostMesh m;
+    m.nTri = nTri;
+    std::memcpy(m.box.mn, box, 12);
+    std::memcpy(m.box.mx, box + 3, 12);
+    m.reflectiveness = material->reflectiveness;
+    m.refractionIndex = material->refractionIndex;
+    m.flags = (material->useTexture ? MESH_USE_TEXTURE : 0) | (material->interpolateNormals ? MESH_INTERP_NORMALS : 0) |
+              (material->transparent ? MESH_TRANSPARENT : 0);
+    if (material->useTexture) {
+        m.texW = material->texW; m.texH = material->texH;
+        m.texels.assign(material->argb, material->argb + (size_t)m.texW * (size_t)m.texH);
+    }
+    int rc = buildMeshOctree(tris, nTri, itemThreshold, m.tree, c->err);
+    if (rc != XNART_OK) return rc;
+    packTriangles(tris, nTri, m.triI, m.triS);
+    *meshIdOut = (int32_t)c->meshes.size();
+    c->meshes.push_back(std::move(m));
+    c->built = false;
+    return XNART_OK;
+}
+
+int32_t xnart_add_object(XnartCtx* c, const int32_t* meshIds, int32_t nMesh, const float world[16],
+                         const float inverseWorld[16], const float localBox[6], int32_t* objIdOut) {
+    if (!c || !meshIds || nMesh < 0 || !world || !inverseWorld || !localBox || !objIdOut)
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: bad arguments");
+    std::lock_guard<std::mutex> lk(c->renderMutex);
+    HostObj o;
+    for (int i = 0; i < nMesh; i++) {
+        if (meshIds[i] < 0 || meshIds[i] >= (int)c->meshes.size()) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: bad mesh id");
+        o.meshIds.push_back(meshIds[i]);
+    }
+    std::memcpy(o.world, world, 64);
+    std::memcpy(o.inv, inverseWorld, 64);
+    std::memcpy(o.localBox.mn, localBox, 12);
+    std::memcpy(o.localBox.mx, localBox + 3, 12);
+    *objIdOut = (int32_t)c->objs.size();
+    c->objs.push_back(o);
+    c->built = false;
+    return XNART_OK;
+}
+
+int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
+    if (!c || itemThreshold < 0) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_build_scene: bad arguments");
+    std::lock_guard<std::mutex> lk(c->renderMutex);
+    int rc = buildSceneOctree(c->objs, itemThreshold, c->sceneTree, c->err);
+    if (rc != XNART_OK) return rc;
+    c->hasTransparent = false;
+    for (const HostMesh& m : c->meshes) {
+        if (m.flags & MESH_TRANSPARENT) c->hasTransparent = true;
+        if (m.tree.depth > kMaxMeshDepth) return fail(c, XNART_ERR_UNSUPPORTED, "mesh octree deeper than the device traversal stack allows");
+    }
+    if (c->sceneTree.depth > kMaxSceneDepth) return fail(c, XNART_ERR_UNSUPPORTED, "scene octree deeper than the device traversal stack allows");
+    if (c->devs.empty()) { c->built = true; return XNART_OK; }  // host-only context: trees can be exported
+
+    // ---- flatten: all mesh trees, then the scene tree, in one node array -------------------------
+    size_t nNodes = c->sceneTree.nodeCount(), nCons = c->sceneTree.consMax.size() / 3, nRefs = c->sceneTree.refs.size();
+    size_t nTri = 0, nTex = 0, nObjMesh = 0;
+    for (const HostMesh& m : c->meshes) {
+        nNodes += m.tree.nodeCount(); nCons += m.tree.consMax.size() / 3; nRefs += m.tree.refs.size();
+        nTri += (size_t)m.nTri; nTex += m.texels.size();
+    }
+    for (const HostObj& o : c->objs) nObjMesh += o.meshIds.size();
+    if (nNodes > 0x3fffffffULL || nRefs > 0x7fffffffULL || nTri > 0x7fffffffULL / 8)
+        return fail(c, XNART_ERR_UNSUPPORTED, "scene too large for 32-bit node/reference indices");
+    std::vector<float4> nodes(2 * nNodes), cons(nCons), triI(4 * nTri), triS(5 * nTri);
+    std::vector<int> refs(nRefs), objMeshIds(nObjMesh);
+    std::vector<uint32_t> texels(nTex);
+    std::vector<DevMesh> dmeshes(c->meshes.size());
+    std::vector<DevObj> dobjs(c->objs.size());
+    size_t nodeBase = 0, consBase = 0, refBase = 0, triBase = 0, texBase = 0;
+    auto emitTree = [&](const FlatTree& t) {
+        for (size_t n = 0; n < t.nodeCount(); n++) {
+            int w0 = t.w0[n], w1 = t.w1[n];
+            if (w1 >= 0) w0 += (int)refBase;                                   // leaf: global ref position
+            else { w0 += (int)nodeBase; w1 = -1 - ((-1 - w1) + (int)consBase); }  // internal: global child / cons index
+            nodes[2 * (nodeBase + n)] = make_float4(t.lo[3 * n], t.lo[3 * n + 1], t.lo[3 * n + 2], __int_as_float_host(w0));
+            nodes[2 * (nodeBase + n) + 1] = make_float4(t.hi[3 * n], t.hi[3 * n + 1], t.hi[3 * n + 2], __int_as_float_host(w1));
+        }
+        for (size_t k = 0; k < t.consMax.size() / 3; k++)
+            cons[consBase + k] = make_float4(t.consMax[3 * k], t.consMax[3 * k + 1], t.consMax[3 * k + 2], 0.0f);
+        std::copy(t.refs.begin(), t.refs.end(), refs.begin() + (long)refBase);
+        nodeBase += t.nodeCount(); consBase += t.consMax.size() / 3; refBase += t.refs.size();
+    };
+    for (size_t i = 0; i < c->meshes.size(); i++) {
+        const HostMesh& m = c->meshes[i];
+        DevMesh& dm = dmeshes[i];
+        std::memcpy(dm.box, m.box.mn, 12);
+        std::memcpy(dm.box + 3, m.box.mx, 12);
+        dm.rootNode = (int)nodeBase;
+        dm.triBase = (int)triBase;
+        dm.reflectiveness = m.reflectiveness;
+        dm.oneMinusReflectiveness = 1.0f - m.reflectiveness;
+        dm.refractionIndex = m.refractionIndex;
+        dm.flags = m.flags;
+        dm.texOffset = (int)texBase; dm.texW = m.texW; dm.texH = m.texH; dm._pad = 0;
+        emitTree(m.tree);
+        std::memcpy(&triI[4 * triBase], m.triI.data(), m.triI.size() * sizeof(float));
+        std::memcpy(&triS[5 * triBase], m.triS.data(), m.triS.size() * sizeof(float));
+        std::copy(m.texels.begin(), m.texels.end(), texels.begin() + (long)texBase);
+        triBase += (size_t)m.nTri; texBase += m.texels.size();
+    }
+    const int sceneRoot = (int)nodeBase;
+    emitTree(c->sceneTree);
+    size_t om = 0;
+    for (size_t i = 0; i < c->objs.size(); i++) {
+        const HostObj& o = c->objs[i];
+        DevObj& d = dobjs[i];
+        std::memcpy(d.world, o.world, 64);
+        std::memcpy(d.inv, o.inv, 64);
+        d.meshStart = (int)om; d.meshCount = (int)o.meshIds.size(); d._pad[0] = d._pad[1] = 0;
+        for (int id : o.meshIds) objMeshIds[om++] = id;
+    }
+    for (DeviceState& d : c->devs) {
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        freeScene(d);
+        CU_TRY(c, uploadVec(&d.nodes, nodes));
+        CU_TRY(c, uploadVec(&d.consMax, cons));
+        CU_TRY(c, uploadVec(&d.refs, refs));
+        CU_TRY(c, uploadVec(&d.triI, triI));
+        CU_TRY(c, uploadVec(&d.triS, triS));
+        CU_TRY(c, uploadVec(&d.meshes, dmeshes));
+        CU_TRY(c, uploadVec(&d.objs, dobjs));
+        CU_TRY(c, uploadVec(&d.objMeshIds, objMeshIds));
+        CU_TRY(c, uploadVec(&d.texels, texels));
+        d.scene.nodes = d.nodes; d.scene.consMax = d.consMax; d.scene.refs = d.refs;
+        d.scene.triI = d.triI; d.scene.triS = d.triS; d.scene.meshes = d.meshes; d.scene.objs = d.objs;
+        d.scene.objMeshIds = d.objMeshIds; d.scene.texels = d.texels;
+        d.scene.sceneRoot = sceneRoot; d.scene.nMeshes = (int)dmeshes.size(); d.scene.nObjs = (int)dobjs.size();
+    }
+    c->built = true;
+    return XNART_OK;
+}
+
+int32_t xnart_set_lights(XnartCtx* c, const XnartLight* lights, int32_t n) {
+    if (!c || n < 0 || (n > 0 && !lights)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_set_lights: bad arguments");
+    if (n > kMaxLights) return fail(c, XNART_ERR_UNSUPPORTED, "too many lights");
+    for (int i = 0; i < n; i++)
+        if (lights[i].kind != XNART_LIGHT_SPOT && lights[i].kind != XNART_LIGHT_DIRECTIONAL)
+            return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_set_lights: unknown light kind");
+    std::lock_guard<std::mutex> lk(c->renderMutex);
+    c->lights.assign(lights, lights + n);
+    c->lightsDirty = true;
+    return XNART_OK;
+}
+
+static int uploadLights(XnartCtx* c) {
+    std::vector<DevLight> dl(std::max<size_t>(c->lights.size(), 1));
+    for (size_t i = 0; i < c->lights.size(); i++) {
+        const XnartLight& s = c->lights[i];
+        DevLight& L = dl[i];
+        L.kind = s.kind;
+        L.px = s.position[0]; L.py = s.position[1]; L.pz = s.position[2];
+        L.dx = s.direction[0]; L.dy = s.direction[1]; L.dz = s.direction[2];
+        L.cr = s.color[0]; L.cg = s.color[1]; L.cb = s.color[2];
+        L.intensity = s.intensity;
+        L.angleCosine = (float)std::cos((double)(s.spotAngle * 0.5f));                       // SpotLight.cs:25
+        L.powDen = std::pow((double)(1.0f - L.angleCosine), (double)s.decayExponent);       // SpotLight.cs:54
+    }
+    for (DeviceState& d : c->devs) {
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        cudaFree(d.lights);
+        d.lights = nullptr;
+        CU_TRY(c, cudaMalloc(&d.lights, dl.size() * sizeof(DevLight)));
+        CU_TRY(c, cudaMemcpy(d.lights, dl.data(), dl.size() * sizeof(DevLight), cudaMemcpyHostToDevice));
+    }
+    c->lightsDirty = false;
+    return XNART_OK;
+}
+
+// rows y of [0,H) owned by a shard
+static int localRowsOf(int H, int shardIndex, int shardCount, int bandRows) {
+    if (shardCount <= 1) return H;
+    int rows = 0;
+    for (int b = shardIndex; b * bandRows < H; b += shardCount) rows += std::min(bandRows, H - b * bandRows);
+    return rows;
+}
+
+static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned rays) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t need = al((size_t)nodes * 16) * 2 + al((size_t)nodes * 8) + al((size_t)nodes * 4) * 2 +
+                  2 * (al((size_t)rays * 16) * 2 + al((size_t)rays * 8));
+    if (need > d.arenaBytes) {
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        cudaFree(d.arenaBlock);
+        d.arenaBlock = nullptr; d.arenaBytes = 0;
+        CU_TRY(c, cudaMalloc(&d.arenaBlock, need));
+        d.arenaBytes = need;
+    }
+    char* p = (char*)d.arenaBlock;
+    auto take = [&](size_t bytes) { char* r = p; p += al(bytes); return r; };
+    DevArena& A = d.arena;
+    A.nodeA = (float4*)take((size_t)nodes * 16);
+    A.nodeB = (float4*)take((size_t)nodes * 16);
+    A.nodeC = (uint2*)take((size_t)nodes * 8);
+    A.color = (uint32_t*)take((size_t)nodes * 4);
+    A.flags = (uint32_t*)take((size_t)nodes * 4);
+    for (int q = 0; q < 2; q++) {
+        A.rayO[q] = (float4*)take((size_t)rays * 16);
+        A.rayD[q] = (float4*)take((size_t)rays * 16);
+        A.rayIgn[q] = (int2*)take((size_t)rays * 8);
+    }
+    A.levelCount = d.levelWords;
+    A.levelBase = d.levelWords + (kMaxLevels + 2);
+    A.overflow = d.levelWords + 2 * (kMaxLevels + 2);
+    A.counters = d.counters;
+    A.nodeCapacity = nodes; A.rayCapacity = rays;
+    d.arenaNodes = nodes; d.arenaRays = rays;
+    return XNART_OK;
+}
+
+static int validateFrame(XnartCtx* c, const XnartFrame* f) {
+    if (!f) return fail(c, XNART_ERR_INVALID_ARGUMENT, "null frame");
+    if (f->vpW <= 0 || f->vpH <= 0) return fail(c, XNART_ERR_INVALID_ARGUMENT, "empty viewport");
+    // Material.LookupUV throws ArgumentException for unknown enum values (Material.cs:85,97)
+    if (f->filtering != XNART_FILTER_POINT && f->filtering != XNART_FILTER_BILINEAR)
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "Value does not fall within the expected range: filtering");
+    if (f->addressMode < XNART_ADDRESS_CLAMP || f->addressMode > XNART_ADDRESS_MIRROR)
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "Value does not fall within the expected range: addressMode");
+    if (f->semantics != XNART_SEMANTICS_XNA40 && f->semantics != XNART_SEMANTICS_MONOGAME)
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "unknown semantics");
+    if (f->maxReflections < 0 || f->maxReflections + 1 > kMaxLevels) return fail(c, XNART_ERR_UNSUPPORTED, "maxReflections out of range");
+    if (f->shardCount > 1 && (f->shardIndex < 0 || f->shardIndex >= f->shardCount || f->shardBandRows <= 0))
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "bad shard parameters");
+    return XNART_OK;
+}
+
+// Enqueue the whole trace loop of one frame shard on `st`, writing full-frame-indexed RGBA8 to devOut.
+static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st) {
+    DevFrame F;
+    {
+        // Viewport.Unproject: Invert(Multiply(Multiply(world = Identity, view), proj)) — once per frame
+        float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, wv[16], wvp[16];
+        multiply44(ident, f.view, wv);
+        multiply44(wv, f.proj, wvp);
+        invert44(wvp, F.inv);
+    }
+    F.vpX = f.vpX; F.vpY = f.vpY; F.vpW = f.vpW; F.vpH = f.vpH;
+    F.minDepth = f.minDepth; F.maxDepth = f.maxDepth;
+    F.maxReflections = f.maxReflections; F.filtering = f.filtering; F.addressMode = f.addressMode; F.semantics = f.semantics;
+    F.shardIndex = f.shardCount > 1 ? f.shardIndex : 0;
+    F.shardCount = f.shardCount > 1 ? f.shardCount : 1;
+    F.shardBandRows = f.shardCount > 1 ? f.shardBandRows : 1;
+    F.nLights = (int)c->lights.size();
+    F._pad = 0;
+    const int D = f.maxReflections;
+    const long long localPixels = (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
+    d.lastPixels = localPixels;
+    d.lastLights = F.nLights;
+    // worst-case arena per pixel: a chain of D+1 path nodes, or a full binary tree when a
+    // transparent material can fork every hit into reflection + refraction (RayTracer.cs:586-702)
+    const double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
+    const double raysPerPixel = c->hasTransparent ? std::ldexp(1.0, D) : 1.0;
+    const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * 80.0 + 64.0;
+    long long chunk = (long long)std::floor((double)c->arenaLimit / bytesPerPixel);
+    chunk = std::min<long long>(chunk, (long long)(4.0e9 / nodesPerPixel));
+    chunk = std::min(chunk, localPixels);
+    if (chunk < 1) return fail(c, XNART_ERR_OUT_OF_MEMORY, "arena limit too small for one pixel at this recursion depth");
+    if (chunk < localPixels && chunk >= 4096) chunk -= chunk % 4096;
+    const unsigned nodeCap = (unsigned)std::min(4.0e9, std::ceil((double)chunk * nodesPerPixel));
+    const unsigned rayCap = (unsigned)std::min(4.0e9, std::ceil((double)chunk * raysPerPixel));
+    int rc = ensureArena(c, d, nodeCap, rayCap);
+    if (rc != XNART_OK) return rc;
+    const int maxBlocks = d.smCount * 8;
+
+    CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
+    CU_TRY(c, cudaEventRecord(d.ev[0], st));
+    for (long long p0 = 0; p0 < localPixels; p0 += chunk) {
+        F.pixelBase = p0;
+        F.chunkPixels = (int)std::min(chunk, localPixels - p0);
+        CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2), st));
+        for (int L = 0; L <= D; L++) {
+            double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
+            CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, st));
+            c->launches++;
+        }
+        for (int L = D - 1; L >= 0; L--) {
+            double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
+            CU_TRY(c, launchResolve(F, d.arena, L, (long long)ub, maxBlocks, devOut, st));
+            c->launches++;
+        }
+        if (D == 0) {
+            CU_TRY(c, launchResolve(F, d.arena, 0, F.chunkPixels, maxBlocks, devOut, st));
+            c->launches++;
+        }
+    }
+    CU_TRY(c, cudaEventRecord(d.ev[2], st));
+    d.lastStream = st;
+    d.countersPending = true;
+    return XNART_OK;
+}
+
+static int collectCounters(XnartCtx* c) {
+    XnartCounters t{};
+    bool any = false;
+    for (DeviceState& d : c->devs) {
+        if (!d.countersPending) continue;
+        any = true;
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaStreamSynchronize(d.lastStream));
+        unsigned long long h[kCounterSlots];
+        unsigned ovf = 0;
+        CU_TRY(c, cudaMemcpy(h, d.counters, sizeof h, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(&ovf, d.arena.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
+        if (ovf) return fail(c, XNART_ERR_OUT_OF_MEMORY, "internal: ray queue overflow");
+        t.pixels += (uint64_t)d.lastPixels;
+        t.raysPrimary += (uint64_t)d.lastPixels;
+        t.hits += h[CTR_HITS];
+        t.raysShadow += h[CTR_HITS] * (uint64_t)d.lastLights;
+        t.raysReflection += h[CTR_RAYS_REFLECTION];
+        t.raysRefraction += h[CTR_RAYS_REFRACTION];
+        t.nBox += h[CTR_NBOX]; t.nTriRef += h[CTR_NTRIREF]; t.nTriCulled += h[CTR_NTRICULLED]; t.nTriFull += h[CTR_NTRIFULL];
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[2]) == cudaSuccess) t.msLevels = std::max(t.msLevels, (double)ms);
+        d.countersPending = false;
+    }
+    if (any) {
+        t.msCopy = c->last.msCopy; t.msTotal = c->last.msTotal; t.msResolve = 0;
+        c->last = t;
+    }
+    return XNART_OK;
+}
+
+int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* devOut, void* cudaStream) {
+    if (!c || !devOut) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frame_device: bad arguments");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");  // RayTracer.cs:62-63
+    if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
+    if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
+    int rc = validateFrame(c, frame);
+    if (rc != XNART_OK) return rc;
+    if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
+    DeviceState& d = c->devs[0];
+    CU_TRY(c, cudaSetDevice(d.dev));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : d.stream;
+    c->progress = 0.0f;
+    rc = enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
+    if (rc != XNART_OK) return rc;
+    if (!cudaStream) {
+        CU_TRY(c, cudaStreamSynchronize(st));
+        c->last.msCopy = 0; c->last.msTotal = 0;
+        rc = collectCounters(c);
+        c->last.msTotal = c->last.msLevels;
+    }
+    c->progress = 1.0f;
+    return rc;
+}
+
+int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) {
+    if (!c || !out) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frame: bad arguments");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
+    if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
+    int rc = validateFrame(c, frame);
+    if (rc != XNART_OK) return rc;
+    if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
+    c->progress = 0.0f;
+    const size_t pixels = (size_t)frame->vpW * (size_t)frame->vpH;
+    const int nDev = (int)c->devs.size();
+    // Is the caller's buffer page-locked?  Then the device->host copy can land in it directly.
+    cudaPointerAttributes pa{};
+    bool outPinned = (cudaPointerGetAttributes(&pa, out) == cudaSuccess) && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    // In-process multi-GPU: scanline bands are dealt round-robin to the devices of the context
+    // (RayTracer.cs:49-52 treats scanlines as independent work items); a caller-supplied shard is
+    // subdivided the same way.
+    const bool callerShard = frame->shardCount > 1;
+    if (callerShard && nDev > 1) return fail(c, XNART_ERR_UNSUPPORTED, "caller sharding with a multi-device context");
+    for (int i = 0; i < nDev; i++) {
+        DeviceState& d = c->devs[i];
+        CU_TRY(c, cudaSetDevice(d.dev));
+        if (d.frameBufPixels < pixels) {
+            CU_TRY(c, cudaStreamSynchronize(d.stream));
+            cudaFree(d.frameBuf); d.frameBuf = nullptr; d.frameBufPixels = 0;
+            CU_TRY(c, cudaMalloc(&d.frameBuf, pixels * 4));
+            d.frameBufPixels = pixels;
+        }
+        if (!outPinned && d.pinnedPixels < pixels) {
+            if (d.pinned) cudaFreeHost(d.pinned);
+            d.pinned = nullptr; d.pinnedPixels = 0;
+            CU_TRY(c, cudaMallocHost(&d.pinned, pixels * 4));
+            d.pinnedPixels = pixels;
+        }
+        XnartFrame f = *frame;
+        if (nDev > 1) { f.shardIndex = i; f.shardCount = nDev; f.shardBandRows = 8; }
+        rc = enqueueFrame(c, d, f, d.frameBuf, d.stream);
+        if (rc != XNART_OK) return rc;
+        // device -> host: only the rows this device owns
+        uint32_t* hostDst = outPinned ? out : d.pinned;
+        const int sc = f.shardCount > 1 ? f.shardCount : 1, br = f.shardCount > 1 ? f.shardBandRows : f.vpH;
+        for (int b = (sc > 1 ? f.shardIndex : 0); (long long)b * br < f.vpH; b += sc) {
+            int y0 = b * br, rows = std::min(br, f.vpH - y0);
+            size_t off = (size_t)y0 * (size_t)f.vpW;
+            CU_TRY(c, cudaMemcpyAsync(hostDst + off, d.frameBuf + off, (size_t)rows * f.vpW * 4, cudaMemcpyDeviceToHost, d.stream));
+        }
+        CU_TRY(c, cudaEventRecord(d.ev[3], d.stream));
+    }
+    double msTotal = 0, msCopy = 0;
+    for (int i = 0; i < nDev; i++) {
+        DeviceState& d = c->devs[i];
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        c->progress = (float)(i + 1) / (float)nDev;
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, d.ev[0], d.ev[3]);
+        cudaEventElapsedTime(&b, d.ev[2], d.ev[3]);
+        msTotal = std::max(msTotal, (double)a); msCopy = std::max(msCopy, (double)b);
+        if (!outPinned) {
+            const int sc = nDev > 1 ? nDev : (callerShard ? frame->shardCount : 1);
+            const int br = nDev > 1 ? 8 : (callerShard ? frame->shardBandRows : frame->vpH);
+            const int si = nDev > 1 ? i : (callerShard ? frame->shardIndex : 0);
+            for (int bnd = si; (long long)bnd * br < frame->vpH; bnd += sc) {
+                int y0 = bnd * br, rows = std::min(br, frame->vpH - y0);
+                size_t off = (size_t)y0 * (size_t)frame->vpW;
+                std::memcpy(out + off, d.pinned + off, (size_t)rows * frame->vpW * 4);
+            }
+        }
+    }
+    c->last.msCopy = msCopy; c->last.msTotal = msTotal;
+    rc = collectCounters(c);
+    c->last.msCopy = msCopy; c->last.msTotal = msTotal;
+    c->progress = 1.0f;
+    return rc;
+}
+
+int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32_t* ignore2, int32_t* objId, int32_t* meshId,
+                         int32_t* triId, float* u, float* v, float* dOut, float* worldPos3) {
+    if (!c || n < 0 || (n > 0 && (!rays6 || !objId || !meshId || !triId || !u || !v || !dOut)))
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_trace_rays: bad arguments");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
+    if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
+    if (n == 0) return XNART_OK;
+    DeviceState& d = c->devs[0];
+    CU_TRY(c, cudaSetDevice(d.dev));
+    float *dr = nullptr, *du = nullptr, *dv = nullptr, *dd = nullptr, *dp = nullptr;
+    int *di = nullptr, *dobj = nullptr, *dmesh = nullptr, *dtri = nullptr;
+    size_t N = (size_t)n;
+    auto cleanup = [&]() { cudaFree(dr); cudaFree(du); cudaFree(dv); cudaFree(dd); cudaFree(dp); cudaFree(di); cudaFree(dobj); cudaFree(dmesh); cudaFree(dtri); };
+#define TR_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(c, XNART_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(_e)); } } while (0)
+    TR_TRY(cudaMalloc(&dr, N * 24)); TR_TRY(cudaMalloc(&du, N * 4)); TR_TRY(cudaMalloc(&dv, N * 4)); TR_TRY(cudaMalloc(&dd, N * 4));
+    TR_TRY(cudaMalloc(&dp, N * 12)); TR_TRY(cudaMalloc(&dobj, N * 4)); TR_TRY(cudaMalloc(&dmesh, N * 4)); TR_TRY(cudaMalloc(&dtri, N * 4));
+    if (ignore2) { TR_TRY(cudaMalloc(&di, N * 8)); TR_TRY(cudaMemcpyAsync(di, ignore2, N * 8, cudaMemcpyHostToDevice, d.stream)); }
+    TR_TRY(cudaMemcpyAsync(dr, rays6, N * 24, cudaMemcpyHostToDevice, d.stream));
+    TR_TRY(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+    TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, d.stream));
+    c->launches++;
+    TR_TRY(cudaMemcpyAsync(objId, dobj, N * 4, cudaMemcpyDeviceToHost, d.stream));
+    TR_TRY(cudaMemcpyAsync(meshId, dmesh, N * 4, cudaMemcpyDeviceToHost, d.stream));
+    TR_TRY(cudaMemcpyAsync(triId, dtri, N * 4, cudaMemcpyDeviceToHost, d.stream));
+    TR_TRY(cudaMemcpyAsync(u, du, N * 4, cudaMemcpyDeviceToHost, d.stream));
+    TR_TRY(cudaMemcpyAsync(v, dv, N * 4, cudaMemcpyDeviceToHost, d.stream));
+    TR_TRY(cudaMemcpyAsync(dOut, dd, N * 4, cudaMemcpyDeviceToHost, d.stream));
+    if (worldPos3) TR_TRY(cudaMemcpyAsync(worldPos3, dp, N * 12, cudaMemcpyDeviceToHost, d.stream));
+    unsigned long long h[kCounterSlots];
+    TR_TRY(cudaMemcpyAsync(h, d.counters, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+    TR_TRY(cudaStreamSynchronize(d.stream));
+#undef TR_TRY
+    cleanup();
+    XnartCounters t{};
+    t.raysPrimary = (uint64_t)n; t.hits = h[CTR_HITS];
+    t.nBox = h[CTR_NBOX]; t.nTriRef = h[CTR_NTRIREF]; t.nTriCulled = h[CTR_NTRICULLED]; t.nTriFull = h[CTR_NTRIFULL];
+    c->last = t;
+    return XNART_OK;
+}
+
+int32_t xnart_get_counters(XnartCtx* c, XnartCounters* out) {
+    if (!c || !out) return XNART_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(c->renderMutex);
+    int rc = collectCounters(c);
+    *out = c->last;
+    return rc;
+}
+
+float xnart_progress(XnartCtx* c) { return c ? c->progress.load() : 0.0f; }
+
+int64_t xnart_kernel_launches(XnartCtx* c) { return c ? c->launches.load() : 0; }
+
+// Page-locked host memory for the frame (so the device->host copy needs no staging).
+void* xnart_alloc_host(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void xnart_free_host(void* p) { if (p) cudaFreeHost(p); }
+
+// Structural export of the flattened octrees (host data; works in a host-only context).
+// which: 0 = mesh tree `id`, 1 = scene tree.
+int32_t xnart_debug_tree_info(XnartCtx* c, int32_t which, int32_t id, int32_t* nNodes, int32_t* nRefs, int32_t* nCons, int32_t* depth) {
+    if (!c) return XNART_ERR_INVALID_ARGUMENT;
+    const FlatTree* t = which == 1 ? &c->sceneTree : ((id >= 0 && id < (int)c->meshes.size()) ? &c->meshes[id].tree : nullptr);
+    if (!t) return fail(c, XNART_ERR_INVALID_ARGUMENT, "bad tree id");
+    *nNodes = (int32_t)t->nodeCount(); *nRefs = (int32_t)t->refs.size(); *nCons = (int32_t)(t->consMax.size() / 3); *depth = t->depth;
+    return XNART_OK;
+}
+int32_t xnart_debug_tree_dump(XnartCtx* c, int32_t which, int32_t id, float* lo3, float* hi3, int32_t* w0, int32_t* w1,
+                              float* consMax3, int32_t* refs) {
+    if (!c) return XNART_ERR_INVALID_ARGUMENT;
+    const FlatTree* t = which == 1 ? &c->sceneTree : ((id >= 0 && id < (int)c->meshes.size()) ? &c->meshes[id].tree : nullptr);
+    if (!t) return fail(c, XNART_ERR_INVALID_ARGUMENT, "bad tree id");
+    std::memcpy(lo3, t->lo.data(), t->lo.size() * 4);
+    std::memcpy(hi3, t->hi.data(), t->hi.size() * 4);
+    std::memcpy(w0, t->w0.data(), t->w0.size() * 4);
+    std::memcpy(w1, t->w1.data(), t->w1.size() * 4);
+    if (consMax3 && !t->consMax.empty()) std::memcpy(consMax3, t->consMax.data(), t->consMax.size() * 4);
+    if (refs && !t->refs.empty()) std::memcpy(refs, t->refs.data(), t->refs.size() * 4);
+    return XNART_OK;
+}
+
+}  // extern "C"
