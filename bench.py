@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the trace path (BASELINE.json: Mrays/s, frames/s at 1080p).
+
+Own arm (default):   python bench.py --gpus N --steps K --warmup W
+    step   = every rank renders ONE 1920x1080 frame of the Free_crate scene (configs[1]: depth 8,
+             Point+Wrap, 1 spot light) from its own orbit camera — frames of a flythrough are the
+             path's natural multi-GPU axis (weak scaling) — and the finished frames are gathered to
+             rank 0 over NCCL.  Scene resident in HBM, output stays on the device.
+    value  = rays traced by all ranks / device time (CUDA events, max over ranks), Mrays/s
+    e2e    = same metric through the reference-facing C-ABI call xnart_render_frame with HOST
+             buffers: the XnartFrame goes in, the frame comes back to pinned host memory inside the
+             timed region.
+    roofline / cpu_baseline: see DESIGN.md ("Measurement").
+Reference arm:       python bench.py --impl reference ...
+    times the CPU restatement of the reference (oracle, all host threads) on a bounded band of
+    scanlines of the same frames.  The reference's own C# cannot be built here (no mono/dotnet).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+WORKLOAD = "free_crate_1080p_depth8"
+
+
+def orbit_camera(scenes, i, n=64):
+    import math
+
+    rot = 2.0 * math.pi * (i % n) / n
+    return scenes.CameraData((math.sin(rot) * 72.0, 35.0, math.cos(rot) * 72.0), (0.0, 11.8, 0.0))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def alg_bytes(c):
+    """Algorithmic bytes of SURVEY.md §8(d): 40 B per ray + 32 B per slab test + 4 B per triangle
+    reference + 24 B per culled and 48 B per full triangle test + 84 B per shaded hit + 4 B per pixel."""
+    rays = c.raysPrimary + c.raysShadow + c.raysReflection + c.raysRefraction
+    return 40 * rays + 32 * c.nBox + 4 * c.nTriRef + 24 * c.nTriCulled + 48 * c.nTriFull + 84 * c.hits + 4 * c.pixels
+
+
+def alg_flops(c):
+    return 18 * c.nBox + 8 * c.nTriCulled + 51 * c.nTriFull + 120 * c.hits
+
+
+def cpu_baseline(scene, scenes, n_threads, rows, cam_index=0):
+    """Oracle (port of the reference's CPU path) on a band of scanlines; returns Mrays/s, seconds, rays."""
+    from oracle import oracle as O
+
+    o = O.Oracle()
+    scenes.upload(o, scene)
+    f = scene.frame(W, H, camera=orbit_camera(scenes, cam_index))
+    t0 = time.perf_counter()
+    o.render_frame(f, n_threads=n_threads, rows=rows)
+    dt = time.perf_counter() - t0
+    rays = o.counters().rays
+    o.close()
+    return rays / dt / 1e6, dt, rays
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from xna_ray_trace_b200 import scenes
+
+    scene = scenes.crate_scene()
+    cores = os.cpu_count() or 1
+    rows = (H // 2 - 135, H // 2 + 135)  # 270 of 1080 scanlines through the crate: a bounded sample
+    for i in range(args.warmup):
+        cpu_baseline(scene, scenes, cores, (H // 2, H // 2 + 16), i)
+    tot_rays, tot_t = 0, 0.0
+    for i in range(args.steps):
+        _, dt, rays = cpu_baseline(scene, scenes, cores, rows, i)
+        tot_rays += rays
+        tot_t += dt
+    v = tot_rays / tot_t / 1e6
+    frames_equiv = (rows[1] - rows[0]) / H
+    line = {
+        "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "width": W, "height": H, "max_reflections": 8,
+                   "note": "reference C# cannot be built here (no mono/dotnet): CPU restatement (oracle) on host cores"},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                         "sample": "scanlines %d..%d of each 1080p frame (%.0f%% of a frame), %d threads" % (rows[0], rows[1], 100 * frames_equiv, cores)},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": frames_equiv * args.steps / tot_t,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="xnart", choices=["xnart", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from xna_ray_trace_b200 import capi, records, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libxnart has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene = scenes.crate_scene()
+    x = capi.Xnart(devices=(local_rank,))
+    scenes.upload(x, scene)
+
+    frame_dev = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    gathered = [torch.zeros((H, W), dtype=torch.int32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    stream = torch.cuda.current_stream()
+
+    warm = max(args.warmup, 3)
+    # camera matrices are host-side inputs (Camera.View/Projection in the reference): built up front
+    all_frames = [scene.frame(W, H, camera=orbit_camera(scenes, i * world + rank)) for i in range(warm + args.steps)]
+
+    def step(i):
+        x.render_frame_device(all_frames[i], frame_dev.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.gather(frame_dev, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warm):
+        step(i)
+    barrier()
+    rays_per_step = []
+    launches0 = x.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(stream)
+        for i in range(args.steps):
+            step(warm + i)
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = x.kernel_launches() - launches0
+    # rays per frame (device counters are per render; re-render each timed camera outside the timed region)
+    lvl_ms, res_ms = [], []
+    for i in range(args.steps):
+        x.render_frame_device(all_frames[warm + i], frame_dev.data_ptr(), None)
+        c = x.counters()
+        rays_per_step.append(c.rays)
+        lvl_ms.append(c.msLevels)
+        res_ms.append(c.msResolve)
+    my_rays = float(sum(rays_per_step))
+    t = torch.tensor([ms, my_rays], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, total_rays = float(tmax[0]), float(tsum[1])
+    else:
+        total_rays = my_rays
+    value = total_rays / (ms * 1e-3) / 1e6
+
+    # ---- e2e: the C-ABI call with host buffers (H2D of the frame description, D2H of the frame) ----
+    pin = capi.PinnedFrame(H, W)
+    for i in range(3):
+        x.render_frame(all_frames[i], out=pin)
+    barrier()
+    frames = all_frames[warm:]
+    t0 = time.perf_counter()
+    for f in frames:
+        x.render_frame(f, out=pin)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_rays / float(te[0]) / 1e6
+    checksum = int(pin.array.astype(np.uint64).sum())
+
+    # ---- roofline of the dominant kernel (k_level: trace + shade, D+1 launches per frame) ----------
+    roof = None
+    cpu = None
+    if rank == 0:
+        x.set_option(records.OPT_COUNTERS, 1)
+        x.render_frame_device(all_frames[warm], frame_dev.data_ptr(), None)
+        cc = x.counters()
+        x.set_option(records.OPT_COUNTERS, 0)
+        peaks, how = measured_peaks()
+        n_launch = scene.max_reflections + 1
+        lvl = float(np.mean(lvl_ms)) * 1e-3  # seconds of k_level per frame, measured live with CUDA events
+        ab, af = alg_bytes(cc), alg_flops(cc)
+        achieved = ab / lvl / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": how, "kernel": "k_level<false>", "launches_per_step": n_launch,
+                "alg_bytes_per_launch": ab / n_launch, "avg_launch_ms": 1e3 * lvl / n_launch,
+                "alg_fp32_Tops": af / lvl / 1e12, "fp32_noFMA_peak_Tops_nominal": 148 * 128 * 1.965e9 / 1e12,
+                "k_level_share_of_step": float(np.mean(lvl_ms)) / (float(np.mean(lvl_ms)) + float(np.mean(res_ms)) + 1e-12)}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            rows = (H // 2 - 135, H // 2 + 135)
+            v_all, dt_all, _ = cpu_baseline(scene, scenes, cores, rows, warm)
+            v_one, dt_one, _ = cpu_baseline(scene, scenes, 1, (H // 2 - 34, H // 2 + 34), warm)
+            cpu = {"value": v_all, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                   "sample": "scanlines %d..%d of one 1080p frame, %d threads, %.1f s" % (rows[0], rows[1], cores, dt_all),
+                   "single_thread_as_shipped": {"value": v_one, "cores": 1, "seconds": dt_one,
+                                                "note": "RayTracer.cs:99 hard-codes one worker"}}
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "max_reflections": scene.max_reflections,
+                       "triangles": scene.n_triangles, "lights": len(scene.lights), "frames_per_step_per_gpu": 1,
+                       "parallelism": "frames sharded across GPUs, NCCL gather to rank 0" if world > 1 else "single GPU",
+                       "l2": "per-frame path arena (~0.9 GB) exceeds L2; a different camera every step"},
+            "frames_per_s": world * args.steps / (ms * 1e-3),
+            "rays_per_frame": total_rays / (world * max(1, args.steps)),
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 184, "d2h_bytes_per_step": W * H * 4,
+                    "frames_per_s": world * args.steps / float(te[0]), "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    pin.free()
+    x.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -415,6 +415,9 @@ static inline void objectQuery(const Ctx& c, int objIdx, const Ray& ray, int ign
     V3 v1 = transform(ray.p, o.inv);
     V3 v2 = transform(rdp, o.inv);
     Ray tr{v1, normalize(sub(v2, v1))};
+    if (c.mode == MODE_PRUNED && (!std::isfinite(tr.p.x) || !std::isfinite(tr.p.y) || !std::isfinite(tr.p.z) ||
+                                  !std::isfinite(tr.d.x) || !std::isfinite(tr.d.y) || !std::isfinite(tr.d.z)))
+        return;  // same shortcut one level down (object-space ray)
     for (size_t mi = 0; mi < o.meshes.size(); mi++) {
         const Mesh& m = *c.meshes[o.meshes[mi]];
         float tb;
@@ -464,8 +467,14 @@ static bool sceneTraceLiteral(const Ctx& c, const Ray& ray, int ignoreMesh, int 
     return found;
 }
 
+static inline bool finite3(V3 v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); }
+
 static bool sceneTracePruned(const Ctx& c, const Ray& ray, int ignoreMesh, int ignoreTri, Hit& out,
                              LocalCounters& lc) {
+    // A ray with a NaN/inf component can never pass the triangle test (every comparison on the NaN
+    // products is false), so the reference walks the whole tree and reports a miss; the pruned
+    // restatement (and the CUDA kernels) report the miss without doing that work.
+    if (!finite3(ray.p) || !finite3(ray.d)) return false;
     const Tree& tree = c.sceneTree;
     float K = INFINITY;
     bool found = false;

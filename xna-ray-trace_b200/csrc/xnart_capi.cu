@@ -44,6 +44,7 @@ struct DeviceState {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, levels done, resolve done, copy done
     cudaStream_t lastStream = nullptr;
     bool countersPending = false;
+    bool singleChunk = true;
     long long lastPixels = 0;
     int lastLights = 0;
 };
@@ -453,6 +454,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     int rc = ensureArena(c, d, nodeCap, rayCap);
     if (rc != XNART_OK) return rc;
     const int maxBlocks = d.smCount * 8;
+    d.singleChunk = chunk >= localPixels;
 
     CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
     CU_TRY(c, cudaEventRecord(d.ev[0], st));
@@ -465,6 +467,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
             CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, st));
             c->launches++;
         }
+        if (p0 == 0) CU_TRY(c, cudaEventRecord(d.ev[1], st));
         for (int L = D - 1; L >= 0; L--) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
             CU_TRY(c, launchResolve(F, d.arena, L, (long long)ub, maxBlocks, devOut, st));
@@ -501,12 +504,17 @@ static int collectCounters(XnartCtx* c) {
         t.raysReflection += h[CTR_RAYS_REFLECTION];
         t.raysRefraction += h[CTR_RAYS_REFRACTION];
         t.nBox += h[CTR_NBOX]; t.nTriRef += h[CTR_NTRIREF]; t.nTriCulled += h[CTR_NTRICULLED]; t.nTriFull += h[CTR_NTRIFULL];
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[2]) == cudaSuccess) t.msLevels = std::max(t.msLevels, (double)ms);
+        float ms = 0, ms2 = 0;
+        if (d.singleChunk) {
+            if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]) == cudaSuccess) t.msLevels = std::max(t.msLevels, (double)ms);
+            if (cudaEventElapsedTime(&ms2, d.ev[1], d.ev[2]) == cudaSuccess) t.msResolve = std::max(t.msResolve, (double)ms2);
+        } else if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[2]) == cudaSuccess) {
+            t.msLevels = std::max(t.msLevels, (double)ms);  // chunks interleave level and resolve kernels
+        }
         d.countersPending = false;
     }
     if (any) {
-        t.msCopy = c->last.msCopy; t.msTotal = c->last.msTotal; t.msResolve = 0;
+        t.msCopy = c->last.msCopy; t.msTotal = c->last.msTotal;
         c->last = t;
     }
     return XNART_OK;
@@ -531,7 +539,7 @@ int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* de
         CU_TRY(c, cudaStreamSynchronize(st));
         c->last.msCopy = 0; c->last.msTotal = 0;
         rc = collectCounters(c);
-        c->last.msTotal = c->last.msLevels;
+        c->last.msTotal = c->last.msLevels + c->last.msResolve;
     }
     c->progress = 1.0f;
     return rc;
