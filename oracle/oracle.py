@@ -111,8 +111,9 @@ class Oracle:
         arr = make_light_array(lights)
         self._check(self._l.xo_set_lights(self._h, arr, C.c_int32(len(lights))))
 
-    def render_frame(self, frame, n_threads=1, rows=None):
-        out = np.zeros((frame.vpH, frame.vpW), dtype=np.uint32)
+    def render_frame(self, frame, n_threads=1, rows=None, out=None):
+        if out is None:
+            out = np.zeros((frame.vpH, frame.vpW), dtype=np.uint32)
         y0, y1 = rows if rows is not None else (0, frame.vpH)
         self._check(self._l.xo_render_rows(self._h, C.byref(frame), _p(out), C.c_int32(n_threads), C.c_int32(y0), C.c_int32(y1)))
         return out

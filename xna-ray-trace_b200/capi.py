@@ -14,7 +14,7 @@ from .records import (TRIANGLE_DTYPE, XNART_ERR_BUSY, XNART_ERR_INVALID_ARGUMENT
                       f32_array, make_light_array, make_material)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libxnart.so")
+LIB_PATH = os.environ.get("XNART_LIB") or os.path.join(_PKG, "libxnart.so")  # XNART_LIB: development override
 _lib = None
 
 

@@ -14,6 +14,10 @@
 #include "kernels.h"
 #include "trace.cuh"
 
+#ifndef XN_LEVEL_MIN_BLOCKS
+#define XN_LEVEL_MIN_BLOCKS 2
+#endif
+
 namespace xn {
 
 __device__ __forceinline__ unsigned warpSum(unsigned v) {
@@ -51,7 +55,7 @@ __device__ __forceinline__ V3 unproject(const DevFrame& F, float sx, float sy, f
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+__global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     const unsigned count = (level == 0) ? (unsigned)F.chunkPixels : A.levelCount[level];
     const unsigned base = (level == 0) ? 0u : A.levelBase[level];
     const unsigned nextBase = base + count;
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(256) k_resolve(DevFrame F, DevArena A, int lev
 
 // Batch form of ISpatialManager.GetRayIntersection for parity tests.
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_trace_rays(DevScene S, const float* __restrict__ rays6, long long n,
+__global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_trace_rays(DevScene S, const float* __restrict__ rays6, long long n,
                                                     const int* __restrict__ ignore2, int* __restrict__ objId,
                                                     int* __restrict__ meshId, int* __restrict__ triId, float* __restrict__ u,
                                                     float* __restrict__ v, float* __restrict__ d, float* __restrict__ pos3,
