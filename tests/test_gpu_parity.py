@@ -47,14 +47,20 @@ def assert_hits_identical(a, b):
         assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
 
 
+# kernel schedules (XNART_OPT_TRAVERSAL): 1 = one thread per ray, 2 = one octet (8 lanes) per ray
+SCHEDULES = [1, 2]
+
+
+@pytest.mark.parametrize("schedule", SCHEDULES)
 @pytest.mark.parametrize("name", ["crate", "spheres", "grid", "soup", "many"])
-def test_trace_rays_bit_exact(X, oracle_mod, name):
+def test_trace_rays_bit_exact(X, oracle_mod, name, schedule):
     s = make_scene(name)
     f = s.frame(96, 64)
     rays = np.concatenate([oracle_mod.primary_rays(f), random_rays(20000, 16.0, 11)])
     o = oracle_mod.Oracle()
     scenes.upload(o, s)
     x = X.Xnart()
+    x.set_option(records.OPT_TRAVERSAL, schedule)
     scenes.upload(x, s)
     want, got = o.trace_rays(rays), x.trace_rays(rays)
     assert (want["tri"] >= 0).sum() > 100
@@ -71,14 +77,16 @@ def test_trace_rays_bit_exact(X, oracle_mod, name):
     x.close()
 
 
+@pytest.mark.parametrize("schedule", SCHEDULES)
 @pytest.mark.parametrize("name,wh", [("crate", (320, 240)), ("spheres", (256, 256)), ("grid", (240, 135)),
                                      ("soup", (160, 120)), ("many", (240, 180))])
-def test_frames_identical(X, oracle_mod, name, wh):
+def test_frames_identical(X, oracle_mod, name, wh, schedule):
     s = make_scene(name)
     f = s.frame(*wh)
     o = oracle_mod.Oracle()
     scenes.upload(o, s)
     x = X.Xnart()
+    x.set_option(records.OPT_TRAVERSAL, schedule)
     scenes.upload(x, s)
     want = o.render_frame(f, n_threads=8)
     got = x.render_frame(f)
@@ -90,8 +98,9 @@ def test_frames_identical(X, oracle_mod, name, wh):
     x.close()
 
 
+@pytest.mark.parametrize("schedule", SCHEDULES)
 @pytest.mark.parametrize("name", ["crate", "grid", "many"])
-def test_counters_equal_oracle_pruned(X, oracle_mod, name):
+def test_counters_equal_oracle_pruned(X, oracle_mod, name, schedule):
     """The instrumented kernels count exactly the work of the oracle's pruned traversal
     (N_box_min, triangle references, culled and full triangle tests: SURVEY.md §8d)."""
     s = make_scene(name)
@@ -100,6 +109,7 @@ def test_counters_equal_oracle_pruned(X, oracle_mod, name):
     scenes.upload(o, s)
     x = X.Xnart()
     x.set_option(records.OPT_COUNTERS, 1)
+    x.set_option(records.OPT_TRAVERSAL, schedule)
     scenes.upload(x, s)
     assert np.array_equal(o.render_frame(f, n_threads=4), x.render_frame(f))
     oc, xc = o.counters(), x.counters()

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--frames", type=int, default=5)
     ap.add_argument("--check", action="store_true", help="compare a band of scanlines with the oracle")
     ap.add_argument("--count", action="store_true", help="run the instrumented kernels once and print work counters")
+    ap.add_argument("--traversal", type=int, default=0, help="XNART_OPT_TRAVERSAL: 0 auto, 1 thread per ray, 2 octet per ray")
     args = ap.parse_args()
 
     from xna_ray_trace_b200 import capi, records, scenes
@@ -45,6 +46,7 @@ def main():
         s.max_reflections = args.depth
     t_gen = time.time() - t0
     x = capi.Xnart()
+    x.set_option(records.OPT_TRAVERSAL, args.traversal)
     t0 = time.time()
     scenes.upload(x, s)
     t_up = time.time() - t0

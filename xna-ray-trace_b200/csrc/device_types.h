@@ -19,14 +19,17 @@
 //            stores object ids.
 //
 // Triangles (Triangle.cs:14-25) are split into a 64-byte intersection record and an 80-byte
-// shading record, both arrays of float4 read with 128-bit loads:
-//   triI[4t+0] = (n.xyz, 0)  triI[4t+1] = (v1.xyz, 0)  triI[4t+2] = (E1.xyz, 0)  triI[4t+3] = (E2.xyz, 0)
-//       n = surfaceNormal comes first so a triangle rejected by the backface test
-//       (RayExtensions.cs:49-51) costs one 32-byte sector; a 64-byte aligned record never
-//       straddles more than two sectors.  E1 = v2 - v1, E2 = v3 - v1 are computed once on the
-//       host in binary32 — bit-identical to the per-test recomputation at RayExtensions.cs:54-55.
+// shading record, both arrays of float4 read with 128-bit loads.
+//   leafTri[4p+0] = (n.xyz, bits(triangle index))  [4p+1] = (v1.xyz, 0)  [4p+2] = (E1.xyz, 0)  [4p+3] = (E2.xyz, 0)
+//       ONE RECORD PER LEAF REFERENCE, at the reference's own position p in refs[]: a leaf's
+//       triangles are one contiguous run of 64-byte records, so the walk needs no dependent
+//       index load (refs[p] -> triangle -> record) and can issue all four loads of a record at
+//       once.  Triangles referenced by several leaves (vertex-containment binning,
+//       MeshOctree.cs:226-228) are stored once per reference (about 2.2x on the 1M-triangle grid).
+//       n = surfaceNormal; E1 = v2 - v1, E2 = v3 - v1 are computed once on the host in binary32 —
+//       bit-identical to the per-test recomputation at RayExtensions.cs:54-55.
 //   triS[5t+0] = (uv1.xy, uv2.xy) triS[5t+1] = (uv3.xy, n1.xy) triS[5t+2] = (n1.z, n2.xyz)
-//   triS[5t+3] = (n3.xyz, color.x) triS[5t+4] = (color.yzw, 0)
+//   triS[5t+3] = (n3.xyz, color.x) triS[5t+4] = (color.yzw, 0)      (by triangle, read once per shaded hit)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -43,7 +46,7 @@ constexpr int kBuilderDepthGuard = 64;  // same guard as the oracle: deeper -> X
 struct DevMesh {
     float box[6];        // Mesh.MeshBoundingBox (Mesh.cs:34-39 prefilter)
     int rootNode;        // global node index of the MeshOctree root
-    int triBase;         // first triangle of this mesh in triI/triS
+    int triBase;         // first triangle of this mesh in triS
     float reflectiveness;
     float oneMinusReflectiveness;  // 1.0f - Reflectiveness (RayTracer.cs:584), hoisted
     float refractionIndex;
@@ -73,7 +76,7 @@ struct DevScene {
     const float4* nodes;
     const float4* consMax;
     const int* refs;
-    const float4* triI;
+    const float4* leafTri;
     const float4* triS;
     const DevMesh* meshes;
     const DevObj* objs;

@@ -1,21 +1,28 @@
 // kernels.cu — the wavefront trace loop of libxnart.so (hand-written CUDA, sm_100a).
 //
 // One frame = one launch sequence on one stream, no host round trip in between:
-//   k_level<L = 0>        primary rays generated in-kernel (RayTracer.Render, RayTracer.cs:410-421),
-//                         closest hit, shadow rays, shading; reflection/refraction rays appended to
-//                         the next level's queue with warp-aggregated atomics
-//   k_level<L = 1..D>     same, rays read from the queue (RayTracer.CastRay recursion, :506-737,
-//                         turned into one wave per recursion depth)
-//   k_resolve<L = D-1..0> bottom-up colour resolve; every level packs to an 8-bit Color exactly where
-//                         the reference's recursion does (RayTracer.cs:584,699,705), level 0 writes
-//                         renderTargetData (RayTracer.cs:425)
+//   k_level / k_level_coop, level 0      primary rays generated in-kernel (RayTracer.Render,
+//                         RayTracer.cs:410-421), closest hit, shadow rays, shading; reflection and
+//                         refraction rays appended to the next level's queue with warp-aggregated atomics
+//   k_level / k_level_coop, level 1..D   same, rays read from the queue (the RayTracer.CastRay
+//                         recursion, :506-737, turned into one wave per recursion depth)
+//   k_resolve, level D-1..0   bottom-up colour resolve; every level packs to an 8-bit Color exactly
+//                         where the reference's recursion does (RayTracer.cs:584,699,705), level 0
+//                         writes renderTargetData (RayTracer.cs:425)
 // Queue sizes live in device memory (levelCount/levelBase); every kernel is a grid-stride loop
 // over "however many rays the previous level produced".
+//
+// Two schedules of the same work: k_level walks one ray per thread (best when the octrees are a
+// leaf or two deep, e.g. the 14-triangle crate scene); k_level_coop lets the 8 lanes of an octet
+// walk each ray together (trace.cuh: traceMeshOctet), which keeps deep-tree traversal convergent.
 #include "kernels.h"
 #include "trace.cuh"
 
 #ifndef XN_LEVEL_MIN_BLOCKS
 #define XN_LEVEL_MIN_BLOCKS 2
+#endif
+#ifndef XN_COOP_MIN_BLOCKS
+#define XN_COOP_MIN_BLOCKS 3
 #endif
 
 namespace xn {
@@ -54,174 +61,137 @@ __device__ __forceinline__ V3 unproject(const DevFrame& F, float sx, float sy, f
     return v;
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
-    const unsigned count = (level == 0) ? (unsigned)F.chunkPixels : A.levelCount[level];
-    const unsigned base = (level == 0) ? 0u : A.levelBase[level];
-    const unsigned nextBase = base + count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (level == 0) { A.levelCount[0] = count; A.levelBase[0] = 0u; }
-        A.levelBase[level + 1] = nextBase;
+struct RayIn {
+    V3 o, d;
+    int ignM, ignT;
+    float refIndex;
+};
+
+// Level 0: RayTracer.Render's per-pixel Unproject pair (:412-421).  Level > 0: the queued ray.
+__device__ __forceinline__ RayIn loadRay(const DevFrame& F, const DevArena& A, int level, unsigned idx) {
+    RayIn r;
+    if (level == 0) {
+        int x, y;
+        pixelOf(F, F.pixelBase + idx, x, y);
+        r.o = unproject(F, (float)x, (float)y, 0.0f);
+        V3 farP = unproject(F, (float)x, (float)y, 1.0f);
+        r.d = normalize(sub(farP, r.o));
+        r.ignM = -1; r.ignT = -1; r.refIndex = 1.0f;
+    } else {
+        const int in = level & 1;
+        float4 o4 = A.rayO[in][idx], d4 = A.rayD[in][idx];
+        int2 ig = A.rayIgn[in][idx];
+        r.o = mk(o4.x, o4.y, o4.z); r.refIndex = o4.w;
+        r.d = mk(d4.x, d4.y, d4.z);
+        r.ignM = ig.x; r.ignT = ig.y;
     }
-    const int in = level & 1, outq = in ^ 1;
-    const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
-    Ctr ctr;
-    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
-    unsigned nHits = 0, nRefl = 0, nRefr = 0;
+    return r;
+}
 
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
-        const unsigned node = base + idx;
-        V3 ro, rd0;
-        int ignM = -1, ignT = -1;
-        float refIndex = 1.0f;
-        if (level == 0) {
-            int x, y;
-            pixelOf(F, F.pixelBase + idx, x, y);
-            ro = unproject(F, (float)x, (float)y, 0.0f);
-            V3 farP = unproject(F, (float)x, (float)y, 1.0f);
-            rd0 = normalize(sub(farP, ro));
-        } else {
-            float4 o4 = A.rayO[in][idx], d4 = A.rayD[in][idx];
-            int2 ig = A.rayIgn[in][idx];
-            ro = mk(o4.x, o4.y, o4.z); refIndex = o4.w;
-            rd0 = mk(d4.x, d4.y, d4.z);
-            ignM = ig.x; ignT = ig.y;
-        }
-
-        // q = 0: the closest-hit query of CastRay (:512); q = 1..nLights: IsLightPathObstructed (:465-502).
-        // One call site keeps a single copy of the traversal code in the kernel.
-        Hit h0;
-        V3 N = mk(0.0f, 0.0f, 0.0f), lightResult = mk(0.0f, 0.0f, 0.0f);
-        V3 qo = ro, qd = rd0;
-        int qm = ignM, qt = ignT;
-        float distToLight = 0.0f;
-        bool hit = false;
-        const DevMesh* __restrict__ M = nullptr;
-        int triG = 0;
-        for (int q = 0;; q++) {
-            Hit h;
-            bool ok = traceScene<COUNT>(S, qo, qd, qm, qt, h, ctr);
-            if (q == 0) {
-                if (!ok) break;
-                hit = true;
-                h0 = h;
-                M = &S.meshes[h0.mesh];
-                triG = M->triBase + h0.tri;
-                if (M->flags & MESH_INTERP_NORMALS) {  // :520-527
-                    const float4* __restrict__ T = S.triS + 5 * (size_t)triG;
-                    float4 s1 = __ldg(&T[1]), s2 = __ldg(&T[2]), s3 = __ldg(&T[3]);
-                    V3 n1 = mk(s1.z, s1.w, s2.x), n2 = mk(s2.y, s2.z, s2.w), n3 = mk(s3.x, s3.y, s3.z);
-                    N = normalize(add(add(n1, mul(sub(n2, n1), h0.u)), mul(sub(n3, n1), h0.v)));
-                } else {
-                    float4 n4 = __ldg(&S.triI[4 * (size_t)triG]);
-                    N = mk(n4.x, n4.y, n4.z);
-                }
-            } else {
-                const DevLight L = lights[q - 1];
-                float amount = 0.0f;
-                if (ok && h.d < distToLight) {
-                    const DevMesh* __restrict__ SM = &S.meshes[h.mesh];
-                    amount = (SM->flags & MESH_TRANSPARENT) ? __ldg(&S.triS[5 * (size_t)(SM->triBase + h.tri) + 4]).z : 1.0f;
-                }
-                if (amount != 1.0f)  // :538-541
-                    lightResult = add(lightResult, mul(lightForFragment(L, h0.pos, N), 1.0f - amount));
-            }
-            if (q == F.nLights) break;
-            // shadow ray towards light q (no epsilon offset, ignoring only the hit triangle: Q4)
-            const DevLight L = lights[q];
-            V3 dir;
-            if (L.kind == XNART_LIGHT_SPOT) {
-                dir = sub(mk(L.px, L.py, L.pz), h0.pos);
-                distToLight = length(dir);
-                dir = normalize(dir);
-            } else {
-                dir = neg(mk(L.dx, L.dy, L.dz));
-                distToLight = FLT_MAX;
-            }
-            qo = h0.pos; qd = dir; qm = h0.mesh; qt = h0.tri;
-        }
-
-        if (!hit) {
-            A.color[node] = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);  // :732
-            A.flags[node] = 0u;
-            continue;
-        }
-        nHits++;
-
-        // surface colour (:568-581 / :711-724)
+// fragment normal (:520-531)
+__device__ __forceinline__ V3 fragmentNormal(const DevScene& S, const DevMesh* __restrict__ M, int triG, const Hit& h) {
+    if (M->flags & MESH_INTERP_NORMALS) {
         const float4* __restrict__ T = S.triS + 5 * (size_t)triG;
-        V3 surf;
-        float4 s3 = __ldg(&T[3]), s4 = __ldg(&T[4]);
-        if (M->flags & MESH_USE_TEXTURE) {
-            float4 s0 = __ldg(&T[0]), s1 = __ldg(&T[1]);
-            float ax = s0.z - s0.x, ay = s0.w - s0.y;  // uv2 - uv1
-            float bx = s1.x - s0.x, by = s1.y - s0.y;  // uv3 - uv1
-            float tu = (s0.x + (ax * h0.u)) + (bx * h0.v);
-            float tv = (s0.y + (ay * h0.u)) + (by * h0.v);
-            surf = lookupUV(S.texels + M->texOffset, M->texW, M->texH, tu, tv, F.addressMode, F.filtering);
-        } else {
-            surf = mk(s3.w, s4.x, s4.y);
-        }
-
-        if (last) {
-            A.color[node] = packColor(mulv(lightResult, surf), F.semantics);  // :726
-            A.flags[node] = 0u;
-            continue;
-        }
-
-        // reflection ray (:547-559) — always cast, whatever the reflectiveness (Q9)
-        V3 rdir = normalize(reflect(rd0, N));
-        unsigned reflChild, refrChild = 0xFFFFFFFFu;
-        {
-            cg::coalesced_group g = cg::coalesced_threads();
-            unsigned b = 0;
-            if (g.thread_rank() == 0) b = atomicAdd(&A.levelCount[level + 1], g.size());
-            unsigned slot = g.shfl(b, 0) + g.thread_rank();
-            reflChild = nextBase + slot;
-            if (slot < A.rayCapacity && reflChild < A.nodeCapacity) {
-                A.rayO[outq][slot] = make_float4(h0.pos.x, h0.pos.y, h0.pos.z, refIndex);
-                A.rayD[outq][slot] = make_float4(rdir.x, rdir.y, rdir.z, 0.0f);
-                A.rayIgn[outq][slot] = make_int2(h0.mesh, h0.tri);
-            } else {
-                *A.overflow = 1u;
-            }
-            nRefl++;
-        }
-        const float alphaW = s4.z;  // triangle.color.W
-        if (M->flags & MESH_TRANSPARENT) {
-            // refraction (:656-698), double-precision island for the Snell term
-            float n1, n2;
-            if (refIndex == M->refractionIndex) { n1 = 1.0f; n2 = refIndex; }
-            else { n1 = M->refractionIndex; n2 = 1.0f; }
-            float cos1 = dot(N, neg(rd0));
-            float k = n1 / n2;
-            double ratio = (double)k, c1 = (double)cos1;
-            float cos2 = (float)sqrt(1.0 - (ratio * ratio) * (1.0 - (c1 * c1)));
-            V3 refr;
-            float w = (k * cos1) - cos2;
-            if (cos1 >= 0.0f) refr = add(mul(rd0, k), mul(N, w));
-            else refr = sub(mul(rd0, k), mul(N, w));
-            V3 fdir = normalize(refr);
-            cg::coalesced_group g = cg::coalesced_threads();
-            unsigned b = 0;
-            if (g.thread_rank() == 0) b = atomicAdd(&A.levelCount[level + 1], g.size());
-            unsigned slot = g.shfl(b, 0) + g.thread_rank();
-            refrChild = nextBase + slot;
-            if (slot < A.rayCapacity && refrChild < A.nodeCapacity) {
-                A.rayO[outq][slot] = make_float4(h0.pos.x, h0.pos.y, h0.pos.z, n2);
-                A.rayD[outq][slot] = make_float4(fdir.x, fdir.y, fdir.z, 0.0f);
-                A.rayIgn[outq][slot] = make_int2(h0.mesh, h0.tri);
-            } else {
-                *A.overflow = 1u;
-            }
-            nRefr++;
-        }
-        A.nodeA[node] = make_float4(lightResult.x, lightResult.y, lightResult.z, M->oneMinusReflectiveness);
-        A.nodeB[node] = make_float4(surf.x, surf.y, surf.z, alphaW);
-        A.nodeC[node] = make_uint2(reflChild, refrChild);
-        A.flags[node] = 1u;
+        float4 s1 = __ldg(&T[1]), s2 = __ldg(&T[2]), s3 = __ldg(&T[3]);
+        V3 n1 = mk(s1.z, s1.w, s2.x), n2 = mk(s2.y, s2.z, s2.w), n3 = mk(s3.x, s3.y, s3.z);
+        return normalize(add(add(n1, mul(sub(n2, n1), h.u)), mul(sub(n3, n1), h.v)));
     }
+    float4 n4 = __ldg(&S.leafTri[4 * (size_t)h.key]);
+    return mk(n4.x, n4.y, n4.z);
+}
 
+// shadow ray towards a light (:467-482): no epsilon offset, ignoring only the hit triangle (Q4)
+__device__ __forceinline__ V3 shadowDir(const DevLight& L, V3 pos, float& distToLight) {
+    if (L.kind == XNART_LIGHT_SPOT) {
+        V3 dir = sub(mk(L.px, L.py, L.pz), pos);
+        distToLight = length(dir);
+        return normalize(dir);
+    }
+    distToLight = FLT_MAX;
+    return neg(mk(L.dx, L.dy, L.dz));
+}
+
+// IsLightPathObstructed's verdict (:485-501) folded into the light sum (:537-541)
+__device__ __forceinline__ V3 addLight(const DevScene& S, const DevLight& L, bool shadowHit, const Hit& sh, float distToLight,
+                                       V3 pos, V3 N, V3 lightResult) {
+    float amount = 0.0f;
+    if (shadowHit && sh.d < distToLight) {
+        const DevMesh* __restrict__ SM = &S.meshes[sh.mesh];
+        amount = (SM->flags & MESH_TRANSPARENT) ? __ldg(&S.triS[5 * (size_t)(SM->triBase + sh.tri) + 4]).z : 1.0f;
+    }
+    if (amount != 1.0f) lightResult = add(lightResult, mul(lightForFragment(L, pos, N), 1.0f - amount));
+    return lightResult;
+}
+
+__device__ __forceinline__ unsigned appendRay(const DevArena& A, int level, int outq, unsigned nextBase, V3 o, V3 d, float refIndex,
+                                              int mesh, int tri) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned b = 0;
+    if (g.thread_rank() == 0) b = atomicAdd(&A.levelCount[level + 1], g.size());
+    const unsigned slot = g.shfl(b, 0) + g.thread_rank();
+    const unsigned child = nextBase + slot;
+    if (slot < A.rayCapacity && child < A.nodeCapacity) {
+        A.rayO[outq][slot] = make_float4(o.x, o.y, o.z, refIndex);
+        A.rayD[outq][slot] = make_float4(d.x, d.y, d.z, 0.0f);
+        A.rayIgn[outq][slot] = make_int2(mesh, tri);
+    } else {
+        *A.overflow = 1u;
+    }
+    return child;
+}
+
+// Everything CastRay does after the light loop (:545-727): surface colour, the path node, and the
+// reflection / refraction rays of the next level.
+__device__ __forceinline__ void finishHit(const DevScene& S, const DevFrame& F, const DevArena& A, int level, bool last, unsigned node,
+                                          unsigned nextBase, const Hit& h0, const DevMesh* __restrict__ M, int triG, V3 N,
+                                          V3 lightResult, V3 rd0, float refIndex, unsigned& nRefl, unsigned& nRefr) {
+    const float4* __restrict__ T = S.triS + 5 * (size_t)triG;
+    V3 surf;
+    float4 s3 = __ldg(&T[3]), s4 = __ldg(&T[4]);
+    if (M->flags & MESH_USE_TEXTURE) {  // :568-575
+        float4 s0 = __ldg(&T[0]), s1 = __ldg(&T[1]);
+        float ax = s0.z - s0.x, ay = s0.w - s0.y;  // uv2 - uv1
+        float bx = s1.x - s0.x, by = s1.y - s0.y;  // uv3 - uv1
+        float tu = (s0.x + (ax * h0.u)) + (bx * h0.v);
+        float tv = (s0.y + (ay * h0.u)) + (by * h0.v);
+        surf = lookupUV(S.texels + M->texOffset, M->texW, M->texH, tu, tv, F.addressMode, F.filtering);
+    } else {
+        surf = mk(s3.w, s4.x, s4.y);
+    }
+    if (last) {
+        A.color[node] = packColor(mulv(lightResult, surf), F.semantics);  // :726
+        A.flags[node] = 0u;
+        return;
+    }
+    const int outq = (level & 1) ^ 1;
+    // reflection ray (:547-559) — always cast, whatever the reflectiveness (Q9)
+    V3 rdir = normalize(reflect(rd0, N));
+    unsigned reflChild = appendRay(A, level, outq, nextBase, h0.pos, rdir, refIndex, h0.mesh, h0.tri);
+    unsigned refrChild = 0xFFFFFFFFu;
+    nRefl++;
+    const float alphaW = s4.z;  // triangle.color.W
+    if (M->flags & MESH_TRANSPARENT) {
+        // refraction (:656-698), double-precision island for the Snell term
+        float n1, n2;
+        if (refIndex == M->refractionIndex) { n1 = 1.0f; n2 = refIndex; }
+        else { n1 = M->refractionIndex; n2 = 1.0f; }
+        float cos1 = dot(N, neg(rd0));
+        float k = n1 / n2;
+        double ratio = (double)k, c1 = (double)cos1;
+        float cos2 = (float)sqrt(1.0 - (ratio * ratio) * (1.0 - (c1 * c1)));
+        float w = (k * cos1) - cos2;
+        V3 refr = (cos1 >= 0.0f) ? add(mul(rd0, k), mul(N, w)) : sub(mul(rd0, k), mul(N, w));
+        refrChild = appendRay(A, level, outq, nextBase, h0.pos, normalize(refr), n2, h0.mesh, h0.tri);
+        nRefr++;
+    }
+    A.nodeA[node] = make_float4(lightResult.x, lightResult.y, lightResult.z, M->oneMinusReflectiveness);
+    A.nodeB[node] = make_float4(surf.x, surf.y, surf.z, alphaW);
+    A.nodeC[node] = make_uint2(reflChild, refrChild);
+    A.flags[node] = 1u;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void flushCounters(const DevArena& A, const Ctr& ctr, unsigned nHits, unsigned nRefl, unsigned nRefr) {
     // ray statistics: one atomic per warp and counter
     const unsigned lane = threadIdx.x & 31u;
     unsigned sH = warpSum(nHits), sR = warpSum(nRefl), sF = warpSum(nRefr);
@@ -239,6 +209,129 @@ __global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_level(DevScene S, 
             atomicAdd(&A.counters[CTR_NTRIFULL], (unsigned long long)d);
         }
     }
+}
+
+__device__ __forceinline__ void levelHeader(const DevFrame& F, const DevArena& A, int level, unsigned& count, unsigned& base) {
+    count = (level == 0) ? (unsigned)F.chunkPixels : A.levelCount[level];
+    base = (level == 0) ? 0u : A.levelBase[level];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (level == 0) { A.levelCount[0] = count; A.levelBase[0] = 0u; }
+        A.levelBase[level + 1] = base + count;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one thread, one ray
+// ---------------------------------------------------------------------------------------------
+// MINB = resident blocks per SM the register allocation is sized for: 2 (128 registers) suits
+// leaf-sized meshes where the kernel is issue bound; 4 (64 registers, some spilling) suits deep
+// octrees, where the walk is bound by dependent-load latency and more resident warps hide it.
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+    unsigned count, base;
+    levelHeader(F, A, level, count, base);
+    const unsigned nextBase = base + count;
+    const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
+    Ctr ctr;
+    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
+    unsigned nHits = 0, nRefl = 0, nRefr = 0;
+
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        const unsigned node = base + idx;
+        const RayIn ray = loadRay(F, A, level, idx);
+        // q = 0: the closest-hit query of CastRay (:512); q = 1..nLights: IsLightPathObstructed (:465-502).
+        // One call site keeps a single copy of the traversal code in the kernel.
+        Hit h0;
+        V3 N = mk(0.0f, 0.0f, 0.0f), lightResult = mk(0.0f, 0.0f, 0.0f);
+        V3 qo = ray.o, qd = ray.d;
+        int qm = ray.ignM, qt = ray.ignT;
+        float distToLight = 0.0f;
+        bool hit = false;
+        const DevMesh* __restrict__ M = nullptr;
+        int triG = 0;
+        for (int q = 0;; q++) {
+            Hit h;
+            bool ok = traceScene<COUNT>(S, qo, qd, qm, qt, h, ctr);
+            if (q == 0) {
+                if (!ok) break;
+                hit = true;
+                h0 = h;
+                M = &S.meshes[h0.mesh];
+                triG = M->triBase + h0.tri;
+                N = fragmentNormal(S, M, triG, h0);
+            } else {
+                lightResult = addLight(S, lights[q - 1], ok, h, distToLight, h0.pos, N, lightResult);
+            }
+            if (q == F.nLights) break;
+            qd = shadowDir(lights[q], h0.pos, distToLight);
+            qo = h0.pos; qm = h0.mesh; qt = h0.tri;
+        }
+        if (!hit) {
+            A.color[node] = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);  // :732
+            A.flags[node] = 0u;
+            continue;
+        }
+        nHits++;
+        finishHit(S, F, A, level, last, node, nextBase, h0, M, triG, N, lightResult, ray.d, ray.refIndex, nRefl, nRefr);
+    }
+    flushCounters<COUNT>(A, ctr, nHits, nRefl, nRefr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one octet (8 lanes), one ray at a time: every lane still OWNS one ray of the queue (loads it,
+// shades it, emits its children), but all traversal is done through traceSceneCoop, where the 8
+// lanes of an octet serve each other's rays one after the other.  Loops are octet-uniform.
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256, XN_COOP_MIN_BLOCKS) k_level_coop(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+    const Octet g = cg::tiled_partition<8>(cg::this_thread_block());
+    unsigned count, base;
+    levelHeader(F, A, level, count, base);
+    const unsigned nextBase = base + count;
+    const bool last = !(level < F.maxReflections);
+    Ctr ctr;
+    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
+    unsigned nHits = 0, nRefl = 0, nRefr = 0;
+    const unsigned lane8 = threadIdx.x & 7u;
+
+    for (unsigned idx0 = blockIdx.x * blockDim.x + (threadIdx.x & ~7u); idx0 < count; idx0 += gridDim.x * blockDim.x) {
+        const unsigned idx = idx0 + lane8;
+        const bool valid = idx < count;
+        const unsigned node = base + idx;
+        RayIn ray;
+        ray.o = ray.d = mk(0.0f, 0.0f, 0.0f); ray.ignM = ray.ignT = -1; ray.refIndex = 1.0f;
+        if (valid) ray = loadRay(F, A, level, idx);
+
+        Hit h0;
+        h0.obj = h0.mesh = h0.tri = -1; h0.key = 0; h0.u = h0.v = h0.d = 0.0f; h0.pos = mk(0.0f, 0.0f, 0.0f);
+        bool hit = traceSceneCoop<COUNT>(g, S, valid, ray.o, ray.d, ray.ignM, ray.ignT, h0, ctr);
+        V3 N = mk(0.0f, 0.0f, 0.0f), lightResult = mk(0.0f, 0.0f, 0.0f);
+        const DevMesh* __restrict__ M = nullptr;
+        int triG = 0;
+        if (hit) {
+            M = &S.meshes[h0.mesh];
+            triG = M->triBase + h0.tri;
+            N = fragmentNormal(S, M, triG, h0);
+        }
+        for (int q = 0; q < F.nLights; q++) {  // uniform trip count: lanes without a hit just help
+            float distToLight = 0.0f;
+            V3 sd = mk(0.0f, 0.0f, 0.0f);
+            if (hit) sd = shadowDir(lights[q], h0.pos, distToLight);
+            Hit sh;
+            sh.obj = sh.mesh = sh.tri = -1; sh.key = 0; sh.u = sh.v = sh.d = 0.0f; sh.pos = mk(0.0f, 0.0f, 0.0f);
+            bool ok = traceSceneCoop<COUNT>(g, S, hit, h0.pos, sd, h0.mesh, h0.tri, sh, ctr);
+            if (hit) lightResult = addLight(S, lights[q], ok, sh, distToLight, h0.pos, N, lightResult);
+        }
+        if (valid && !hit) {
+            A.color[node] = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);
+            A.flags[node] = 0u;
+        }
+        if (hit) {
+            nHits++;
+            finishHit(S, F, A, level, last, node, nextBase, h0, M, triG, N, lightResult, ray.d, ray.refIndex, nRefl, nRefr);
+        }
+    }
+    flushCounters<COUNT>(A, ctr, nHits, nRefl, nRefr);
 }
 
 // Bottom-up resolve of one level.  Nodes whose colour is final (miss, or deepest level) are left
@@ -272,22 +365,34 @@ __global__ void __launch_bounds__(256) k_resolve(DevFrame F, DevArena A, int lev
     }
 }
 
-// Batch form of ISpatialManager.GetRayIntersection for parity tests.
-template <bool COUNT>
+// Batch form of ISpatialManager.GetRayIntersection for parity tests (both schedules).
+template <bool COUNT, bool COOP>
 __global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_trace_rays(DevScene S, const float* __restrict__ rays6, long long n,
-                                                    const int* __restrict__ ignore2, int* __restrict__ objId,
-                                                    int* __restrict__ meshId, int* __restrict__ triId, float* __restrict__ u,
-                                                    float* __restrict__ v, float* __restrict__ d, float* __restrict__ pos3,
-                                                    unsigned long long* __restrict__ counters) {
+                                                                         const int* __restrict__ ignore2, int* __restrict__ objId,
+                                                                         int* __restrict__ meshId, int* __restrict__ triId,
+                                                                         float* __restrict__ u, float* __restrict__ v, float* __restrict__ d,
+                                                                         float* __restrict__ pos3, unsigned long long* __restrict__ counters) {
+    const Octet g = cg::tiled_partition<8>(cg::this_thread_block());
     Ctr ctr;
     ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
     unsigned nHits = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        V3 ro = mk(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]);
-        V3 rd = mk(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]);
-        int im = ignore2 ? ignore2[2 * i] : -1, it = ignore2 ? ignore2[2 * i + 1] : -1;
+    const long long lane8 = threadIdx.x & 7u;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~7u); i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + lane8;
+        const bool valid = i < n;
+        V3 ro = mk(0.0f, 0.0f, 0.0f), rd = mk(0.0f, 0.0f, 0.0f);
+        int im = -1, it = -1;
+        if (valid) {
+            ro = mk(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]);
+            rd = mk(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]);
+            if (ignore2) { im = ignore2[2 * i]; it = ignore2[2 * i + 1]; }
+        }
         Hit h;
-        bool ok = traceScene<COUNT>(S, ro, rd, im, it, h, ctr);
+        h.obj = h.mesh = h.tri = -1; h.key = 0; h.u = h.v = h.d = 0.0f; h.pos = mk(0.0f, 0.0f, 0.0f);
+        bool ok;
+        if (COOP) ok = traceSceneCoop<COUNT>(g, S, valid, ro, rd, im, it, h, ctr);
+        else ok = valid && traceScene<COUNT>(S, ro, rd, im, it, h, ctr);
+        if (!valid) continue;
         if (ok) nHits++;
         objId[i] = ok ? h.obj : -1; meshId[i] = ok ? h.mesh : -1; triId[i] = ok ? h.tri : -1;
         u[i] = ok ? h.u : 0.0f; v[i] = ok ? h.v : 0.0f; d[i] = ok ? h.d : 0.0f;
@@ -318,10 +423,18 @@ static inline int gridFor(long long n, int maxBlocks) {
 }
 
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
-                        long long upperBound, int maxBlocks, bool count, cudaStream_t st) {
+                        long long upperBound, int maxBlocks, bool count, bool coop, bool deep, cudaStream_t st) {
     int grid = gridFor(upperBound, maxBlocks);
-    if (count) k_level<true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
-    else k_level<false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    if (coop) {
+        if (count) k_level_coop<true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level_coop<false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    } else if (deep) {
+        if (count) k_level<true, 4><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, 4><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    } else {
+        if (count) k_level<true, XN_LEVEL_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, XN_LEVEL_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    }
     return cudaGetLastError();
 }
 
@@ -334,10 +447,15 @@ cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long 
 
 cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
-                            int maxBlocks, bool count, cudaStream_t st) {
+                            int maxBlocks, bool count, bool coop, cudaStream_t st) {
     int grid = gridFor(n, maxBlocks);
-    if (count) k_trace_rays<true><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
-    else k_trace_rays<false><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+    if (coop) {
+        if (count) k_trace_rays<true, true><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+        else k_trace_rays<false, true><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+    } else {
+        if (count) k_trace_rays<true, false><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+        else k_trace_rays<false, false><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+    }
     return cudaGetLastError();
 }
 

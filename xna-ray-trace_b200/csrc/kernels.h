@@ -8,9 +8,11 @@
 namespace xn {
 
 // One wave of the trace loop: closest hit + shadow rays + shading for every ray of `level`.
-// upperBound only sizes the grid (the real count is read on the device).
+// upperBound only sizes the grid (the real count is read on the device).  coop selects the octet
+// schedule (8 lanes walk one ray together) instead of one thread per ray; deep selects the
+// high-occupancy (64-register) build of the per-thread kernel.
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
-                        long long upperBound, int maxBlocks, bool count, cudaStream_t st);
+                        long long upperBound, int maxBlocks, bool count, bool coop, bool deep, cudaStream_t st);
 
 // Bottom-up colour resolve of one level; level 0 writes the frame.
 cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long long upperBound, int maxBlocks,
@@ -19,6 +21,6 @@ cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long 
 // Batch closest-hit queries (xnart_trace_rays).
 cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
-                            int maxBlocks, bool count, cudaStream_t st);
+                            int maxBlocks, bool count, bool coop, cudaStream_t st);
 
 }  // namespace xn

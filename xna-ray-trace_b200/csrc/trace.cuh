@@ -84,6 +84,7 @@ __device__ __forceinline__ bool slab(float3 mn, float3 mx, const RayPre& r, floa
 
 struct MeshHit {
     int tri;       // mesh-relative triangle index, -1 = none
+    int key;       // position of the winning leaf reference in refs[] / leafTri[]
     float u, v, d;
 };
 
@@ -115,17 +116,18 @@ __device__ __forceinline__ bool traceMesh(const DevScene& S, int rootNode, int t
             bool lf = false;
             float ld = FLT_MAX, lu = 0.0f, lv = 0.0f;
             int lt = -1, lk = 0;
-            const int* __restrict__ refs = S.refs + w0;
+            const float4* __restrict__ R = S.leafTri + 4 * (size_t)w0;
             for (int i = 0; i < w1; i++) {
-                int ti = __ldg(&refs[i]);
+                // all four loads of the record are issued together (one round trip); a back-facing
+                // triangle wastes three of them, which costs L1 bandwidth the kernel has to spare
+                const float4* __restrict__ T4 = R + 4 * (size_t)i;
+                float4 n4 = __ldg(&T4[0]), a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
+                const int ti = __float_as_int(n4.w);
                 if (COUNT) ctr.nTriRef++;
                 if (ti == ignoreTri) continue;  // ignoreTriangle != triangles[i] (reference identity)
-                const float4* __restrict__ T4 = S.triI + 4 * (size_t)(triBase + ti);
-                float4 n4 = __ldg(&T4[0]);
                 // dot(surfaceNormal, D) > 0 -> back face (RayExtensions.cs:48-51)
                 if (dot(mk(n4.x, n4.y, n4.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; continue; }
                 if (COUNT) ctr.nTriFull++;
-                float4 a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
                 V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z);
                 V3 T = sub(r.o, mk(a.x, a.y, a.z));
                 V3 P = cross(r.d, E2);
@@ -184,19 +186,147 @@ __device__ __forceinline__ bool traceMesh(const DevScene& S, int rootNode, int t
         }
         if (!got) break;
     }
-    out.tri = btri; out.u = bu; out.v = bv; out.d = bd;
+    out.tri = btri; out.key = bkey; out.u = bu; out.v = bv; out.d = bd;
     return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MeshOctree.GetRayIntersection, cooperative form: the 8 lanes of an octet walk ONE ray together.
+//
+// The per-thread walk above diverges badly on deep trees (on the 1M-triangle grid ncu shows ~9 of
+// 32 lanes active: one lane is in a 50-triangle leaf while its neighbours test child boxes).  Here
+// every step is uniform across the octet: an internal step slab-tests the node's 8 children at
+// once (lane j takes the child at front-to-back position j, i.e. child j ^ octant; the 8 x 32 B
+// child block is one contiguous 256-byte read), `ballot` yields the mask of accepted children, and
+// the walk keeps ONE entry per tree level (child block, pending mask, each lane's own entry
+// distance) instead of a stack of nodes; a leaf step tests 8 triangles at a time.  Same visiting
+// order, same K rule and same tie-break as the per-thread walk, so results and work counters are
+// identical; only the lane-level schedule differs.
+// ---------------------------------------------------------------------------------------------
+typedef cg::thread_block_tile<8> Octet;
+constexpr int kMeshLevels = kMaxMeshDepth + 2;
+
+template <bool COUNT>
+__device__ __forceinline__ bool traceMeshOctet(const Octet& g, const DevScene& S, int rootNode, int triBase, const RayPre& r,
+                                               int ignoreTri, MeshHit& out, Ctr& ctr) {
+    const int lane = (int)g.thread_rank();
+    const float4* __restrict__ nodes = S.nodes;
+    float lvT[kMeshLevels];
+    int lvBase[kMeshLevels];
+    unsigned lvMask[kMeshLevels];
+    float K = INFINITY;
+    bool found = false;      // uniform
+    bool rv = false;         // this lane holds a candidate of the current K group
+    float bd = 0.0f, bu = 0.0f, bv = 0.0f;
+    int btri = -1, bkey = 0;
+
+    float4 lo = __ldg(&nodes[2 * rootNode]), hi = __ldg(&nodes[2 * rootNode + 1]);
+    float t0;
+    if (COUNT && lane == 0) ctr.nBox++;
+    if (!slab(make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z), r, t0)) return false;
+    int level = -1;
+    int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
+    float tcur = t0;
+    for (;;) {
+        if (w1 >= 0) {
+            // ---- leaf: 8 triangles per step; each lane keeps the best of the ones it tested
+            bool lf = false;
+            float ld = FLT_MAX, lu = 0.0f, lv = 0.0f;
+            int lt = -1, lk = 0;
+            const float4* __restrict__ R = S.leafTri + 4 * (size_t)w0;
+            for (int i = lane; i < w1; i += 8) {
+                const float4* __restrict__ T4 = R + 4 * (size_t)i;
+                float4 n4 = __ldg(&T4[0]), a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
+                const int ti = __float_as_int(n4.w);
+                if (COUNT) ctr.nTriRef++;
+                if (ti == ignoreTri) continue;
+                if (dot(mk(n4.x, n4.y, n4.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; continue; }
+                if (COUNT) ctr.nTriFull++;
+                V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z);
+                V3 T = sub(r.o, mk(a.x, a.y, a.z));
+                V3 P = cross(r.d, E2);
+                V3 Q = cross(T, E1);
+                float row1 = dot(Q, E2), row2 = dot(P, T), row3 = dot(Q, r.d);
+                float inv = 1.0f / dot(P, E1);
+                float dist = inv * row1, uu = inv * row2, vv = inv * row3;
+                // within a lane positions increase, so strict `<` keeps the earliest of equal distances
+                if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f && dist < ld) {
+                    ld = dist; lu = uu; lv = vv; lt = ti; lk = w0 + i; lf = true;
+                }
+            }
+            if (g.any(lf)) {
+                if (!found || tcur < K) {  // this leaf opens a nearer group: older candidates are void
+                    found = true; K = tcur;
+                    rv = lf; bd = ld; bu = lu; bv = lv; btri = lt; bkey = lk;
+                } else if (tcur == K && lf && (!rv || ld < bd || (ld == bd && lk < bkey))) {
+                    rv = true; bd = ld; bu = lu; bv = lv; btri = lt; bkey = lk;
+                }
+            }
+        } else {
+            // ---- internal: lane j tests the child at front-to-back position j
+            const int c = w0 + (lane ^ r.oct);
+            float4 clo = __ldg(&nodes[2 * c]), chi = __ldg(&nodes[2 * c + 1]);
+            float tc;
+            if (COUNT) ctr.nBox++;
+            bool keep = slab(make_float3(clo.x, clo.y, clo.z), make_float3(chi.x, chi.y, chi.z), r, tc);
+            keep = keep && (!(tc > K) || __float_as_int(chi.w) < 0);
+            unsigned mask = g.ballot(keep);
+            if (mask) { level++; lvT[level] = tc; lvBase[level] = w0; lvMask[level] = mask; }
+        }
+        // ---- next node: nearest pending child of the deepest level that still has one
+        bool got = false;
+        while (level >= 0) {
+            unsigned mask = lvMask[level];
+            if (!mask) { level--; continue; }
+            const int j = __ffs((int)mask) - 1;
+            lvMask[level] = mask & (mask - 1u);
+            const float tn = g.shfl(lvT[level], j);
+            const int n = lvBase[level] + (j ^ r.oct);
+            float4 nlo = __ldg(&nodes[2 * n]), nhi = __ldg(&nodes[2 * n + 1]);
+            const int nw1 = __float_as_int(nhi.w);
+            if (tn > K) {
+                if (nw1 >= 0) continue;
+                float4 cm = __ldg(&S.consMax[-1 - nw1]);
+                float tcns;
+                bool h = slab(make_float3(nlo.x, nlo.y, nlo.z), make_float3(cm.x, cm.y, cm.z), r, tcns);
+                if (h && tcns > K) continue;
+            }
+            w0 = __float_as_int(nlo.w); w1 = nw1; tcur = tn;
+            got = true;
+            break;
+        }
+        if (!got) break;
+    }
+    if (!found) return false;
+    // minimum (distance, position) over the lanes' candidates; every lane ends with the same winner
+    float d = rv ? bd : INFINITY;
+    int key = rv ? bkey : INT_MAX, src = lane;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        float d2 = g.shfl_xor(d, o);
+        int k2 = g.shfl_xor(key, o), s2 = g.shfl_xor(src, o);
+        if (d2 < d || (d2 == d && k2 < key)) { d = d2; key = k2; src = s2; }
+    }
+    out.d = d;
+    out.key = key;
+    out.u = g.shfl(bu, src);
+    out.v = g.shfl(bv, src);
+    out.tri = g.shfl(btri, src);
+    return true;
 }
 
 struct Hit {
     int obj, mesh, tri;
+    int key;  // position of the hit triangle's leaf reference (its 64-byte record in leafTri)
     float u, v, d;
     V3 pos;  // worldPosition
 };
 
 // Per-object block of OctreeSpatialManager.GetRayIntersection (OctreeSpatialManager.cs:347-428).
-template <bool COUNT>
-__device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
+// COOP: called by all 8 lanes of an octet with identical arguments; everything but the mesh walk
+// is computed redundantly (and counted once).
+template <bool COUNT, bool COOP>
+__device__ __forceinline__ void objectQuery(const Octet& g, const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
                                             float& minDistance, bool& found, Hit& best, Ctr& ctr) {
     const DevObj* __restrict__ O = &S.objs[objIdx];
     // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (:358-364)
@@ -211,14 +341,16 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
         int meshId = __ldg(&S.objMeshIds[ms + mi]);
         const DevMesh* __restrict__ M = &S.meshes[meshId];
         float tb;
-        if (COUNT) ctr.nBox++;
+        if (COUNT && (!COOP || g.thread_rank() == 0)) ctr.nBox++;
         // Mesh.RayIntersects (Mesh.cs:34-39)
         if (!slab(make_float3(M->box[0], M->box[1], M->box[2]), make_float3(M->box[3], M->box[4], M->box[5]), r, tb)) continue;
         MeshHit mh;
         int ign = (ignMesh == meshId) ? ignTri : -1;
-        if (traceMesh<COUNT>(S, M->rootNode, M->triBase, r, ign, mh, ctr) && mh.d < minDistance) {
+        const bool ok = COOP ? traceMeshOctet<COUNT>(g, S, M->rootNode, M->triBase, r, ign, mh, ctr)
+                             : traceMesh<COUNT>(S, M->rootNode, M->triBase, r, ign, mh, ctr);
+        if (ok && mh.d < minDistance) {
             minDistance = mh.d;
-            best.obj = objIdx; best.mesh = meshId; best.tri = mh.tri;
+            best.obj = objIdx; best.mesh = meshId; best.tri = mh.tri; best.key = mh.key;
             best.u = mh.u; best.v = mh.v; best.d = mh.d;
             found = true;
         }
@@ -229,19 +361,20 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
 // OctreeSpatialManager.GetRayIntersection.  Same group/early-exit semantics one level up; with
 // <= itemTreshold (20) objects the tree is the root leaf alone.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-__device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
+template <bool COUNT, bool COOP>
+__device__ __forceinline__ bool traceSceneT(const Octet& g, const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
     if (!finite3(ro) || !finite3(rd)) return false;
+    const bool cnt = COUNT && (!COOP || g.thread_rank() == 0);  // uniform work is counted once per octet
     const float4* __restrict__ nodes = S.nodes;
     RayPre r = prepRay(ro, rd);
     float4 lo = __ldg(&nodes[2 * S.sceneRoot]), hi = __ldg(&nodes[2 * S.sceneRoot + 1]);
     float t0;
-    if (COUNT) ctr.nBox++;
+    if (cnt) ctr.nBox++;
     if (!slab(make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z), r, t0)) return false;
     int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
     bool found = false;
     Hit best;
-    best.obj = best.mesh = best.tri = -1; best.u = best.v = best.d = 0.0f;
+    best.obj = best.mesh = best.tri = -1; best.key = 0; best.u = best.v = best.d = 0.0f;
     StackEntry stack[kSceneStack];
     float K = INFINITY;
     float bestD = 0.0f;
@@ -255,12 +388,12 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
             float ld = FLT_MAX;
             bool lf = false;
             Hit lh;
-            lh.obj = lh.mesh = lh.tri = -1; lh.u = lh.v = lh.d = 0.0f;
+            lh.obj = lh.mesh = lh.tri = -1; lh.key = 0; lh.u = lh.v = lh.d = 0.0f;
             int lkey = 0;
             for (int i = 0; i < w1; i++) {
                 const float before = ld;
                 const bool fb = lf;
-                objectQuery<COUNT>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
+                objectQuery<COUNT, COOP>(g, S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
                 if (lf && (!fb || ld < before)) lkey = w0 + i;
             }
             if (lf) {
@@ -275,7 +408,7 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
                 int c = w0 + (i ^ oct);
                 float4 clo = __ldg(&nodes[2 * c]), chi = __ldg(&nodes[2 * c + 1]);
                 float tc;
-                if (COUNT) ctr.nBox++;
+                if (cnt) ctr.nBox++;
                 if (slab(make_float3(clo.x, clo.y, clo.z), make_float3(chi.x, chi.y, chi.z), r, tc)) {
                     if (!(tc > K) || __float_as_int(chi.w) < 0) { stack[sp].node = c; stack[sp].t = tc; sp++; }
                 }
@@ -303,14 +436,41 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
     }
     if (found) {
         // objectSpacePosition = v1 + (v2-v1)*u + (v3-v1)*v (MeshOctree.cs:310-312); world = Po * World (:441-443)
-        const DevMesh* __restrict__ M = &S.meshes[best.mesh];
-        const float4* __restrict__ T4 = S.triI + 4 * (size_t)(M->triBase + best.tri);
+        const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)best.key;
         float4 a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
         V3 po = add(add(mk(a.x, a.y, a.z), mul(mk(b.x, b.y, b.z), best.u)), mul(mk(c.x, c.y, c.z), best.v));
         best.pos = transform43(po, S.objs[best.obj].world);
         out = best;
     }
     return found;
+}
+
+// One thread, one ray.
+template <bool COUNT>
+__device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
+    const Octet g = cg::tiled_partition<8>(cg::this_thread_block());
+    return traceSceneT<COUNT, false>(g, S, ro, rd, ignMesh, ignTri, out, ctr);
+}
+
+// Every lane of the octet brings (at most) one ray; the octet walks them one after the other, all
+// 8 lanes working on the same ray.  Must be called by all 8 lanes together; `want` says whether
+// this lane has a ray.  Returns this lane's own result.
+template <bool COUNT>
+__device__ __forceinline__ bool traceSceneCoop(const Octet& g, const DevScene& S, bool want, V3 ro, V3 rd, int ignMesh,
+                                               int ignTri, Hit& out, Ctr& ctr) {
+    unsigned pending = g.ballot(want);
+    bool myOk = false;
+    while (pending) {
+        const int src = __ffs((int)pending) - 1;
+        pending &= pending - 1u;
+        V3 o = mk(g.shfl(ro.x, src), g.shfl(ro.y, src), g.shfl(ro.z, src));
+        V3 d = mk(g.shfl(rd.x, src), g.shfl(rd.y, src), g.shfl(rd.z, src));
+        const int im = g.shfl(ignMesh, src), it = g.shfl(ignTri, src);
+        Hit h;
+        const bool ok = traceSceneT<COUNT, true>(g, S, o, d, im, it, h, ctr);
+        if ((int)g.thread_rank() == src) { myOk = ok; if (ok) out = h; }
+    }
+    return myOk;
 }
 
 // ---------------------------------------------------------------------------------------------

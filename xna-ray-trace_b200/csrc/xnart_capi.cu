@@ -28,7 +28,7 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     // scene
     float4* nodes = nullptr; float4* consMax = nullptr; int* refs = nullptr;
-    float4* triI = nullptr; float4* triS = nullptr;
+    float4* leafTri = nullptr; float4* triS = nullptr;
     DevMesh* meshes = nullptr; DevObj* objs = nullptr; int* objMeshIds = nullptr; uint32_t* texels = nullptr;
     DevLight* lights = nullptr; int nLightsUploaded = -1;
     DevScene scene{};
@@ -74,6 +74,8 @@ struct XnartCtx {
     bool countKernels = false;
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
+    int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
+    int maxMeshDepth = 0;
     std::atomic<int64_t> launches{0};
     XnartCounters last{};
 };
@@ -97,9 +99,9 @@ static int fail(XnartCtx* c, int code, const std::string& msg) {
 
 static void freeScene(DeviceState& d) {
     cudaSetDevice(d.dev);
-    cudaFree(d.nodes); cudaFree(d.consMax); cudaFree(d.refs); cudaFree(d.triI); cudaFree(d.triS);
+    cudaFree(d.nodes); cudaFree(d.consMax); cudaFree(d.refs); cudaFree(d.leafTri); cudaFree(d.triS);
     cudaFree(d.meshes); cudaFree(d.objs); cudaFree(d.objMeshIds); cudaFree(d.texels);
-    d.nodes = d.consMax = d.triI = d.triS = nullptr; d.refs = nullptr; d.meshes = nullptr; d.objs = nullptr;
+    d.nodes = d.consMax = d.leafTri = d.triS = nullptr; d.refs = nullptr; d.meshes = nullptr; d.objs = nullptr;
     d.objMeshIds = nullptr; d.texels = nullptr;
 }
 
@@ -177,6 +179,9 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
         case XNART_OPT_SEMANTICS:
             if (value != XNART_SEMANTICS_XNA40) return fail(c, XNART_ERR_UNSUPPORTED, "only XNA 4.0 slab semantics are implemented on the device");
             c->traceSemantics = (int)value; return XNART_OK;
+        case XNART_OPT_TRAVERSAL:
+            if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
+            c->traversalMode = (int)value; return XNART_OK;
         default: return fail(c, XNART_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -236,7 +241,9 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     int rc = buildSceneOctree(c->objs, itemThreshold, c->sceneTree, c->err);
     if (rc != XNART_OK) return rc;
     c->hasTransparent = false;
+    c->maxMeshDepth = 0;
     for (const HostMesh& m : c->meshes) {
+        c->maxMeshDepth = std::max(c->maxMeshDepth, m.tree.depth);
         if (m.flags & MESH_TRANSPARENT) c->hasTransparent = true;
         if (m.tree.depth > kMaxMeshDepth) return fail(c, XNART_ERR_UNSUPPORTED, "mesh octree deeper than the device traversal stack allows");
     }
@@ -253,7 +260,8 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     for (const HostObj& o : c->objs) nObjMesh += o.meshIds.size();
     if (nNodes > 0x3fffffffULL || nRefs > 0x7fffffffULL || nTri > 0x7fffffffULL / 8)
         return fail(c, XNART_ERR_UNSUPPORTED, "scene too large for 32-bit node/reference indices");
-    std::vector<float4> nodes(2 * nNodes), cons(nCons), triI(4 * nTri), triS(5 * nTri);
+    size_t nMeshRefs = nRefs - c->sceneTree.refs.size();
+    std::vector<float4> nodes(2 * nNodes), cons(nCons), leafTri(4 * nMeshRefs), triS(5 * nTri);
     std::vector<int> refs(nRefs), objMeshIds(nObjMesh);
     std::vector<uint32_t> texels(nTex);
     std::vector<DevMesh> dmeshes(c->meshes.size());
@@ -284,8 +292,20 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         dm.refractionIndex = m.refractionIndex;
         dm.flags = m.flags;
         dm.texOffset = (int)texBase; dm.texW = m.texW; dm.texH = m.texH; dm._pad = 0;
+        const size_t firstRef = refBase;
         emitTree(m.tree);
-        std::memcpy(&triI[4 * triBase], m.triI.data(), m.triI.size() * sizeof(float));
+        // one intersection record per leaf reference, at the reference's own position
+        {
+            const long long nr = (long long)m.tree.refs.size();
+            const float* src = m.triI.data();
+#pragma omp parallel for schedule(static) if (nr > 65536)
+            for (long long k = 0; k < nr; k++) {
+                const int ti = m.tree.refs[(size_t)k];
+                float4* dst = &leafTri[4 * (firstRef + (size_t)k)];
+                std::memcpy(dst, src + 16 * (size_t)ti, 64);
+                dst[0].w = __int_as_float_host(ti);
+            }
+        }
         std::memcpy(&triS[5 * triBase], m.triS.data(), m.triS.size() * sizeof(float));
         std::copy(m.texels.begin(), m.texels.end(), texels.begin() + (long)texBase);
         triBase += (size_t)m.nTri; texBase += m.texels.size();
@@ -308,14 +328,14 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         CU_TRY(c, uploadVec(&d.nodes, nodes));
         CU_TRY(c, uploadVec(&d.consMax, cons));
         CU_TRY(c, uploadVec(&d.refs, refs));
-        CU_TRY(c, uploadVec(&d.triI, triI));
+        CU_TRY(c, uploadVec(&d.leafTri, leafTri));
         CU_TRY(c, uploadVec(&d.triS, triS));
         CU_TRY(c, uploadVec(&d.meshes, dmeshes));
         CU_TRY(c, uploadVec(&d.objs, dobjs));
         CU_TRY(c, uploadVec(&d.objMeshIds, objMeshIds));
         CU_TRY(c, uploadVec(&d.texels, texels));
         d.scene.nodes = d.nodes; d.scene.consMax = d.consMax; d.scene.refs = d.refs;
-        d.scene.triI = d.triI; d.scene.triS = d.triS; d.scene.meshes = d.meshes; d.scene.objs = d.objs;
+        d.scene.leafTri = d.leafTri; d.scene.triS = d.triS; d.scene.meshes = d.meshes; d.scene.objs = d.objs;
         d.scene.objMeshIds = d.objMeshIds; d.scene.texels = d.texels;
         d.scene.sceneRoot = sceneRoot; d.scene.nMeshes = (int)dmeshes.size(); d.scene.nObjs = (int)dobjs.size();
     }
@@ -401,6 +421,16 @@ static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned ray
     return XNART_OK;
 }
 
+// Octet schedule when some MeshOctree is at least two levels deep (per-thread walks diverge there);
+// one thread per ray for leaf-sized meshes, where the walk is a short loop.
+static bool useCoop(const XnartCtx* c) {
+    if (c->traversalMode == 1) return false;
+    return c->traversalMode == 2;
+}
+// Deep octrees: the walk is latency bound, so the per-thread kernel is launched in its
+// high-occupancy build.
+static bool deepScene(const XnartCtx* c) { return c->maxMeshDepth >= 2; }
+
 static int validateFrame(XnartCtx* c, const XnartFrame* f) {
     if (!f) return fail(c, XNART_ERR_INVALID_ARGUMENT, "null frame");
     if (f->vpW <= 0 || f->vpH <= 0) return fail(c, XNART_ERR_INVALID_ARGUMENT, "empty viewport");
@@ -464,7 +494,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2), st));
         for (int L = 0; L <= D; L++) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
-            CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, st));
+            CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, useCoop(c), deepScene(c), st));
             c->launches++;
         }
         if (p0 == 0) CU_TRY(c, cudaEventRecord(d.ev[1], st));
@@ -644,7 +674,7 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
     if (ignore2) { TR_TRY(cudaMalloc(&di, N * 8)); TR_TRY(cudaMemcpyAsync(di, ignore2, N * 8, cudaMemcpyHostToDevice, d.stream)); }
     TR_TRY(cudaMemcpyAsync(dr, rays6, N * 24, cudaMemcpyHostToDevice, d.stream));
     TR_TRY(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
-    TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, d.stream));
+    TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, useCoop(c), d.stream));
     c->launches++;
     TR_TRY(cudaMemcpyAsync(objId, dobj, N * 4, cudaMemcpyDeviceToHost, d.stream));
     TR_TRY(cudaMemcpyAsync(meshId, dmesh, N * 4, cudaMemcpyDeviceToHost, d.stream));
