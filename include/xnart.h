@@ -113,7 +113,8 @@ enum {
     XNART_OPT_COUNTERS = 1,      /* 0/1: run the instrumented kernels (slower) */
     XNART_OPT_ARENA_BYTES = 2,   /* upper bound for the per-render path arena (default 8 GiB) */
     XNART_OPT_SEMANTICS = 3,     /* default semantics for xnart_trace_rays */
-    XNART_OPT_TRAVERSAL = 4      /* kernel schedule: 0 auto, 1 one thread per ray, 2 one octet (8 lanes) per ray */
+    XNART_OPT_TRAVERSAL = 4,     /* kernel schedule: 0 auto, 1 one thread per ray, 2 one octet (8 lanes) per ray */
+    XNART_OPT_FUSE_FRAME = 5     /* 0/1 (default 1): shallow scenes render a frame in one cooperative launch */
 };
 
 typedef struct XnartCtx XnartCtx;
@@ -155,6 +156,12 @@ int32_t xnart_render_frame(XnartCtx* ctx, const XnartFrame* frame, uint32_t* rgb
  * NULL = the context's own stream, in which case the call returns after completion). */
 int32_t xnart_render_frame_device(XnartCtx* ctx, const XnartFrame* frame,
                                   void* devRgba8Out, void* cudaStream);
+
+/* A camera flythrough (Game1.cs:261-266 orbits the camera and renders frame after frame; the
+ * reference would run RenderInternal + SetData n times): n frames of one viewport size into n
+ * consecutive host frames of vpW*vpH pixels.  Frame f goes to device f % nDevices; on each device
+ * the device->host copy of a frame overlaps the rendering of the next. */
+int32_t xnart_render_frames(XnartCtx* ctx, const XnartFrame* frames, int32_t n, uint32_t* rgba8Out);
 
 /* Batch form of ISpatialManager.GetRayIntersection (ISpatialManager.cs:15;
  * OctreeSpatialManager.cs:312-455) for parity testing: rays6 = n x (position xyz, direction

@@ -68,7 +68,8 @@ def lib():
 
 EXPORTS = [
     "xnart_create", "xnart_destroy", "xnart_last_error", "xnart_set_option", "xnart_add_mesh", "xnart_add_object",
-    "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_trace_rays",
+    "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_render_frames",
+    "xnart_trace_rays",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
     "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump",
 ]
@@ -79,16 +80,16 @@ def _p(a):
 
 
 class PinnedFrame:
-    """A (H, W) uint32 frame in page-locked memory (xnart_alloc_host)."""
+    """A (H, W) — or (N, H, W) with frames=N — uint32 frame buffer in page-locked memory (xnart_alloc_host)."""
 
-    def __init__(self, height, width):
+    def __init__(self, height, width, frames=None):
         self._l = lib()
-        self.nbytes = height * width * 4
+        self.nbytes = height * width * 4 * (frames or 1)
         self.ptr = self._l.xnart_alloc_host(self.nbytes)
         if not self.ptr:
             raise XnartError(7, "xnart_alloc_host failed")
-        buf = (C.c_uint32 * (height * width)).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=np.uint32).reshape(height, width)
+        buf = (C.c_uint32 * (self.nbytes // 4)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.uint32).reshape((height, width) if frames is None else (frames, height, width))
 
     def free(self):
         if self.ptr:
@@ -167,6 +168,19 @@ class Xnart:
         assert arr.dtype == np.uint32 and arr.size == frame.vpH * frame.vpW and arr.flags["C_CONTIGUOUS"]
         self._check(self._l.xnart_render_frame(self._h, C.addressof(frame), arr.ctypes.data))
         return arr
+
+    def render_frames(self, frames, out=None):
+        """xnart_render_frames: a flythrough of n frames into an (n, H, W) uint32 host array (pipelined copies)."""
+        n = len(frames)
+        arr_t = XnartFrame * max(1, n)
+        arr = arr_t(*frames)
+        h, w = frames[0].vpH, frames[0].vpW
+        if out is None:
+            out = np.zeros((n, h, w), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.size == n * h * w and out.flags["C_CONTIGUOUS"]
+        self._l.xnart_render_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        self._check(self._l.xnart_render_frames(self._h, C.cast(arr, C.c_void_p), C.c_int32(n), out.ctypes.data))
+        return out
 
     def render_frame_device(self, frame, dev_ptr, stream=None):
         """xnart_render_frame_device: output stays in device memory at `dev_ptr` (e.g. a torch tensor's data_ptr())."""

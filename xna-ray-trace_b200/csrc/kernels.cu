@@ -24,6 +24,9 @@
 #ifndef XN_COOP_MIN_BLOCKS
 #define XN_COOP_MIN_BLOCKS 3
 #endif
+#ifndef XN_DEEP_MIN_BLOCKS
+#define XN_DEEP_MIN_BLOCKS 4
+#endif
 
 namespace xn {
 
@@ -226,15 +229,13 @@ __device__ __forceinline__ void levelHeader(const DevFrame& F, const DevArena& A
 // MINB = resident blocks per SM the register allocation is sized for: 2 (128 registers) suits
 // leaf-sized meshes where the kernel is issue bound; 4 (64 registers, some spilling) suits deep
 // octrees, where the walk is bound by dependent-load latency and more resident warps hide it.
-template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+template <bool COUNT>
+__device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* __restrict__ lights,
+                                          int level, Ctr& ctr, unsigned& nHits, unsigned& nRefl, unsigned& nRefr) {
     unsigned count, base;
     levelHeader(F, A, level, count, base);
     const unsigned nextBase = base + count;
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
-    Ctr ctr;
-    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
-    unsigned nHits = 0, nRefl = 0, nRefr = 0;
 
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
@@ -274,7 +275,52 @@ __global__ void __launch_bounds__(256, MINB) k_level(DevScene S, DevFrame F, Dev
         nHits++;
         finishHit(S, F, A, level, last, node, nextBase, h0, M, triG, N, lightResult, ray.d, ray.refIndex, nRefl, nRefr);
     }
+}
+
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+    Ctr ctr;
+    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
+    unsigned nHits = 0, nRefl = 0, nRefr = 0;
+    levelBody<COUNT>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
     flushCounters<COUNT>(A, ctr, nHits, nRefl, nRefr);
+}
+
+__device__ __forceinline__ void resolveBody(const DevFrame& F, const DevArena& A, int level, uint32_t* __restrict__ out);
+
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// The whole frame in ONE cooperative launch: level 0..D, then the resolve D-1..0, separated by
+// grid-wide barriers instead of kernel boundaries.  On small scenes the deep levels hold a few
+// thousand rays each and a launch per level costs more than the level itself (ncu launch list,
+// profiles/r01a: 6 tail levels x 10 us + 8 resolve launches on a 0.65 ms frame).  Grid = resident
+// blocks only (cooperative launch), every phase is a grid-stride loop.  stamps[0..2] receive the
+// global timer at start / after the last level / after the resolve, for the per-stage timings.
+template <bool COUNT>
+__global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_frame(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights,
+                                                                     uint32_t* __restrict__ out, unsigned long long* __restrict__ stamps) {
+    cg::grid_group grid = cg::this_grid();
+    Ctr ctr;
+    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
+    unsigned nHits = 0, nRefl = 0, nRefr = 0;
+    const bool stamper = blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamper) stamps[0] = globalTimerNs();
+    const int D = F.maxReflections;
+    for (int level = 0; level <= D; level++) {
+        levelBody<COUNT>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
+        grid.sync();
+    }
+    if (stamper) stamps[1] = globalTimerNs();
+    for (int level = (D > 0 ? D - 1 : 0); level >= 0; level--) {
+        resolveBody(F, A, level, out);
+        if (level > 0) grid.sync();
+    }
+    flushCounters<COUNT>(A, ctr, nHits, nRefl, nRefr);
+    if (stamper) stamps[2] = globalTimerNs();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -336,7 +382,7 @@ __global__ void __launch_bounds__(256, XN_COOP_MIN_BLOCKS) k_level_coop(DevScene
 
 // Bottom-up resolve of one level.  Nodes whose colour is final (miss, or deepest level) are left
 // alone; the others combine their children as CastRay does after its recursive calls return.
-__global__ void __launch_bounds__(256) k_resolve(DevFrame F, DevArena A, int level, uint32_t* __restrict__ out) {
+__device__ __forceinline__ void resolveBody(const DevFrame& F, const DevArena& A, int level, uint32_t* __restrict__ out) {
     const unsigned count = A.levelCount[level];
     const unsigned base = A.levelBase[level];
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
@@ -363,6 +409,10 @@ __global__ void __launch_bounds__(256) k_resolve(DevFrame F, DevArena A, int lev
             out[(size_t)y * (size_t)F.vpW + (size_t)x] = col;  // renderTargetData[y*W + x] (:425)
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_resolve(DevFrame F, DevArena A, int level, uint32_t* __restrict__ out) {
+    resolveBody(F, A, level, out);
 }
 
 // Batch form of ISpatialManager.GetRayIntersection for parity tests (both schedules).
@@ -429,13 +479,31 @@ cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A,
         if (count) k_level_coop<true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
         else k_level_coop<false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
     } else if (deep) {
-        if (count) k_level<true, 4><<<grid, 256, 0, st>>>(S, F, A, lights, level);
-        else k_level<false, 4><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        if (count) k_level<true, XN_DEEP_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, XN_DEEP_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
     } else {
         if (count) k_level<true, XN_LEVEL_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
         else k_level<false, XN_LEVEL_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
     }
     return cudaGetLastError();
+}
+
+// Resident-grid size of k_frame on this device (cooperative launch needs every block resident).
+int frameKernelMaxBlocks(bool count) {
+    int perSm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_frame<true>, 256, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_frame<false>, 256, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return perSm * sms;
+}
+
+cudaError_t launchFrame(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, uint32_t* out,
+                        unsigned long long* stamps, int blocks, bool count, cudaStream_t st) {
+    void* args[] = {(void*)&S, (void*)&F, (void*)&A, (void*)&lights, (void*)&out, (void*)&stamps};
+    const void* fn = count ? (const void*)k_frame<true> : (const void*)k_frame<false>;
+    return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, st);
 }
 
 cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long long upperBound, int maxBlocks,

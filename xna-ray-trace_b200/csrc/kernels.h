@@ -14,6 +14,12 @@ namespace xn {
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
                         long long upperBound, int maxBlocks, bool count, bool coop, bool deep, cudaStream_t st);
 
+// The whole frame (all levels + resolve) in one cooperative launch; `blocks` must not exceed
+// frameKernelMaxBlocks().  stamps = 3 x uint64 device words (global timer at the phase boundaries).
+int frameKernelMaxBlocks(bool count);
+cudaError_t launchFrame(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, uint32_t* out,
+                        unsigned long long* stamps, int blocks, bool count, cudaStream_t st);
+
 // Bottom-up colour resolve of one level; level 0 writes the frame.
 cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long long upperBound, int maxBlocks,
                           uint32_t* out, cudaStream_t st);

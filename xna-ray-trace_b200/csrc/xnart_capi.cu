@@ -38,8 +38,15 @@ struct DeviceState {
     unsigned arenaNodes = 0, arenaRays = 0;
     unsigned* levelWords = nullptr;  // levelCount | levelBase | overflow
     unsigned long long* counters = nullptr;
+    unsigned long long* stamps = nullptr;   // k_frame: global timer at start / levels done / resolve done
+    int frameBlocks = 0, frameBlocksCount = 0;  // resident grid of the cooperative frame kernel
+    bool lastFused = false;
     // output
     uint32_t* frameBuf = nullptr; size_t frameBufPixels = 0;
+    // flythrough pipeline: second frame buffer, copy stream, per-buffer events
+    uint32_t* frameBuf2 = nullptr; size_t frameBuf2Pixels = 0;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evRendered[2] = {nullptr, nullptr}, evCopied[2] = {nullptr, nullptr};
     uint32_t* pinned = nullptr; size_t pinnedPixels = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, levels done, resolve done, copy done
     cudaStream_t lastStream = nullptr;
@@ -74,6 +81,7 @@ struct XnartCtx {
     bool countKernels = false;
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
+    bool fuseFrame = true;   // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
     std::atomic<int64_t> launches{0};
@@ -144,8 +152,17 @@ int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds)
             }
             cudaDeviceGetAttribute(&d.smCount, cudaDevAttrMultiProcessorCount, id);
             for (auto& ev : d.ev) cudaEventCreate(&ev);
+            cudaStreamCreateWithFlags(&d.copyStream, cudaStreamNonBlocking);
+            for (int k = 0; k < 2; k++) {
+                cudaEventCreateWithFlags(&d.evRendered[k], cudaEventDisableTiming);
+                cudaEventCreateWithFlags(&d.evCopied[k], cudaEventDisableTiming);
+            }
             cudaMalloc(&d.levelWords, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2));
             cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounterSlots);
+            cudaMalloc(&d.stamps, sizeof(unsigned long long) * 4);
+            int coopOk = 0;
+            cudaDeviceGetAttribute(&coopOk, cudaDevAttrCooperativeLaunch, id);
+            if (coopOk) { d.frameBlocks = frameKernelMaxBlocks(false); d.frameBlocksCount = frameKernelMaxBlocks(true); }
             cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounterSlots);
             c->devs.push_back(d);
         }
@@ -160,9 +177,12 @@ int32_t xnart_destroy(XnartCtx* c) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
         freeScene(d);
-        cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.levelWords); cudaFree(d.counters); cudaFree(d.frameBuf);
+        cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.levelWords); cudaFree(d.counters); cudaFree(d.stamps); cudaFree(d.frameBuf);
         if (d.pinned) cudaFreeHost(d.pinned);
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
+        for (int k = 0; k < 2; k++) { if (d.evRendered[k]) cudaEventDestroy(d.evRendered[k]); if (d.evCopied[k]) cudaEventDestroy(d.evCopied[k]); }
+        if (d.copyStream) cudaStreamDestroy(d.copyStream);
+        cudaFree(d.frameBuf2);
         cudaStreamDestroy(d.stream);
     }
     delete c;
@@ -179,6 +199,7 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
         case XNART_OPT_SEMANTICS:
             if (value != XNART_SEMANTICS_XNA40) return fail(c, XNART_ERR_UNSUPPORTED, "only XNA 4.0 slab semantics are implemented on the device");
             c->traceSemantics = (int)value; return XNART_OK;
+        case XNART_OPT_FUSE_FRAME: c->fuseFrame = value != 0; return XNART_OK;
         case XNART_OPT_TRAVERSAL:
             if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
             c->traversalMode = (int)value; return XNART_OK;
@@ -448,7 +469,7 @@ static int validateFrame(XnartCtx* c, const XnartFrame* f) {
 }
 
 // Enqueue the whole trace loop of one frame shard on `st`, writing full-frame-indexed RGBA8 to devOut.
-static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st) {
+static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st, bool accumulate = false) {
     DevFrame F;
     {
         // Viewport.Unproject: Invert(Multiply(Multiply(world = Identity, view), proj)) — once per frame
@@ -467,7 +488,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     F._pad = 0;
     const int D = f.maxReflections;
     const long long localPixels = (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
-    d.lastPixels = localPixels;
+    d.lastPixels = accumulate ? d.lastPixels + localPixels : localPixels;
     d.lastLights = F.nLights;
     // worst-case arena per pixel: a chain of D+1 path nodes, or a full binary tree when a
     // transparent material can fork every hit into reflection + refraction (RayTracer.cs:586-702)
@@ -485,13 +506,27 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     if (rc != XNART_OK) return rc;
     const int maxBlocks = d.smCount * 8;
     d.singleChunk = chunk >= localPixels;
+    // Shallow scenes (every MeshOctree a leaf or one split): launch overhead of the deep, nearly
+    // empty levels matters -> one cooperative launch per chunk.  Deep scenes keep one launch per
+    // level in the high-occupancy build of the kernel.
+    const bool fused = c->fuseFrame && !useCoop(c) && !deepScene(c) && d.frameBlocks > 0 && d.frameBlocksCount > 0;
+    d.lastFused = fused;
 
-    CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
-    CU_TRY(c, cudaEventRecord(d.ev[0], st));
+    if (!accumulate) {
+        CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
+        CU_TRY(c, cudaEventRecord(d.ev[0], st));
+    }
     for (long long p0 = 0; p0 < localPixels; p0 += chunk) {
         F.pixelBase = p0;
         F.chunkPixels = (int)std::min(chunk, localPixels - p0);
         CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2), st));
+        if (fused) {
+            // whole chunk in one cooperative launch (levels + resolve, grid barriers in between)
+            const int blocks = c->countKernels ? d.frameBlocksCount : d.frameBlocks;
+            CU_TRY(c, launchFrame(d.scene, F, d.arena, d.lights, devOut, d.stamps, blocks, c->countKernels, st));
+            c->launches++;
+            continue;
+        }
         for (int L = 0; L <= D; L++) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
             CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, useCoop(c), deepScene(c), st));
@@ -535,7 +570,12 @@ static int collectCounters(XnartCtx* c) {
         t.raysRefraction += h[CTR_RAYS_REFRACTION];
         t.nBox += h[CTR_NBOX]; t.nTriRef += h[CTR_NTRIREF]; t.nTriCulled += h[CTR_NTRICULLED]; t.nTriFull += h[CTR_NTRIFULL];
         float ms = 0, ms2 = 0;
-        if (d.singleChunk) {
+        if (d.lastFused && d.singleChunk) {
+            unsigned long long st3[3] = {0, 0, 0};
+            CU_TRY(c, cudaMemcpy(st3, d.stamps, sizeof st3, cudaMemcpyDeviceToHost));
+            t.msLevels = std::max(t.msLevels, (double)(st3[1] - st3[0]) * 1e-6);
+            t.msResolve = std::max(t.msResolve, (double)(st3[2] - st3[1]) * 1e-6);
+        } else if (d.singleChunk) {
             if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]) == cudaSuccess) t.msLevels = std::max(t.msLevels, (double)ms);
             if (cudaEventElapsedTime(&ms2, d.ev[1], d.ev[2]) == cudaSuccess) t.msResolve = std::max(t.msResolve, (double)ms2);
         } else if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[2]) == cudaSuccess) {
@@ -649,6 +689,108 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
     c->last.msCopy = msCopy; c->last.msTotal = msTotal;
     rc = collectCounters(c);
     c->last.msCopy = msCopy; c->last.msTotal = msTotal;
+    c->progress = 1.0f;
+    return rc;
+}
+
+// A camera flythrough (config C4; Game1.cs:261-266 moves the camera on a circle and renders frame
+// after frame): n frames of one viewport size into n consecutive host frames.  Frame f is rendered by
+// device f % nDevices; on each device the device->host copy of a frame overlaps the rendering of
+// the next one (two frame buffers, a copy stream).  Replaces n x RenderInternal + SetData.
+int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, uint32_t* out) {
+    if (!c || n < 0 || (n > 0 && (!frames || !out))) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames: bad arguments");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
+    if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
+    if (n == 0) return XNART_OK;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        if ((rc = validateFrame(c, &frames[i])) != XNART_OK) return rc;
+        if (frames[i].vpW != frames[0].vpW || frames[i].vpH != frames[0].vpH || frames[i].shardCount > 1)
+            return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames: all frames must share one viewport size and be unsharded");
+    }
+    if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
+    c->progress = 0.0f;
+    const size_t pixels = (size_t)frames[0].vpW * (size_t)frames[0].vpH;
+    const int nDev = (int)c->devs.size();
+    cudaPointerAttributes pa{};
+    const bool outPinned = (cudaPointerGetAttributes(&pa, out) == cudaSuccess) && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    for (DeviceState& d : c->devs) {
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        CU_TRY(c, cudaStreamSynchronize(d.copyStream));
+        if (d.frameBufPixels < pixels) {
+            cudaFree(d.frameBuf); d.frameBuf = nullptr; d.frameBufPixels = 0;
+            CU_TRY(c, cudaMalloc(&d.frameBuf, pixels * 4));
+            d.frameBufPixels = pixels;
+        }
+        if (d.frameBuf2Pixels < pixels) {
+            cudaFree(d.frameBuf2); d.frameBuf2 = nullptr; d.frameBuf2Pixels = 0;
+            CU_TRY(c, cudaMalloc(&d.frameBuf2, pixels * 4));
+            d.frameBuf2Pixels = pixels;
+        }
+        if (!outPinned && d.pinnedPixels < 2 * pixels) {
+            if (d.pinned) cudaFreeHost(d.pinned);
+            d.pinned = nullptr; d.pinnedPixels = 0;
+            CU_TRY(c, cudaMallocHost(&d.pinned, 2 * pixels * 4));
+            d.pinnedPixels = 2 * pixels;
+        }
+        d.lastPixels = 0;
+        CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+        CU_TRY(c, cudaEventRecord(d.ev[0], d.stream));
+    }
+    std::vector<int> perDev(nDev, 0);
+    // staged (pageable destination) frames waiting for their host memcpy: (device, slot, frame index)
+    struct Pending { int dev, slot, frame; };
+    std::vector<Pending> pending;
+    auto drain = [&](size_t keep) -> int {
+        while (pending.size() > keep) {
+            Pending p = pending.front();
+            pending.erase(pending.begin());
+            DeviceState& d = c->devs[p.dev];
+            CU_TRY(c, cudaSetDevice(d.dev));
+            CU_TRY(c, cudaEventSynchronize(d.evCopied[p.slot]));
+            std::memcpy(out + (size_t)p.frame * pixels, d.pinned + (size_t)p.slot * pixels, pixels * 4);
+        }
+        return XNART_OK;
+    };
+    for (int f = 0; f < n; f++) {
+        const int di = f % nDev;
+        DeviceState& d = c->devs[di];
+        CU_TRY(c, cudaSetDevice(d.dev));
+        const int slot = perDev[di] & 1;
+        uint32_t* buf = slot ? d.frameBuf2 : d.frameBuf;
+        if (perDev[di] >= 2) {
+            if (!outPinned && (rc = drain((size_t)nDev)) != XNART_OK) return rc;  // the staging slot must be free again
+            CU_TRY(c, cudaStreamWaitEvent(d.stream, d.evCopied[slot], 0));        // buffer free once its copy is done
+        }
+        rc = enqueueFrame(c, d, frames[f], buf, d.stream, /*accumulate=*/true);
+        if (rc != XNART_OK) return rc;
+        CU_TRY(c, cudaEventRecord(d.evRendered[slot], d.stream));
+        CU_TRY(c, cudaStreamWaitEvent(d.copyStream, d.evRendered[slot], 0));
+        uint32_t* dst = outPinned ? out + (size_t)f * pixels : d.pinned + (size_t)slot * pixels;
+        CU_TRY(c, cudaMemcpyAsync(dst, buf, pixels * 4, cudaMemcpyDeviceToHost, d.copyStream));
+        CU_TRY(c, cudaEventRecord(d.evCopied[slot], d.copyStream));
+        if (!outPinned) pending.push_back(Pending{di, slot, f});
+        perDev[di]++;
+    }
+    if (!outPinned && (rc = drain(0)) != XNART_OK) return rc;
+    double msTotal = 0;
+    for (DeviceState& d : c->devs) {
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaEventRecord(d.ev[3], d.copyStream));
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        CU_TRY(c, cudaStreamSynchronize(d.copyStream));
+        float a = 0;
+        if (cudaEventElapsedTime(&a, d.ev[0], d.ev[3]) == cudaSuccess) msTotal = std::max(msTotal, (double)a);
+        d.singleChunk = false;  // per-stage split is not meaningful for a pipelined batch
+        d.lastFused = false;
+    }
+    c->last.msCopy = 0; c->last.msTotal = msTotal;
+    rc = collectCounters(c);
+    c->last.msCopy = 0; c->last.msTotal = msTotal;
     c->progress = 1.0f;
     return rc;
 }
