@@ -113,7 +113,7 @@ enum {
     XNART_OPT_COUNTERS = 1,      /* 0/1: run the instrumented kernels (slower) */
     XNART_OPT_ARENA_BYTES = 2,   /* upper bound for the per-render path arena (default 8 GiB) */
     XNART_OPT_SEMANTICS = 3,     /* default semantics for xnart_trace_rays */
-    XNART_OPT_TRAVERSAL = 4,     /* kernel schedule: 0 auto, 1 one thread per ray, 2 one octet (8 lanes) per ray */
+    XNART_OPT_TRAVERSAL = 4,     /* kernel schedule: 0 auto, 1 one thread per ray, 2 wavefront (persistent trace kernel) */
     XNART_OPT_FUSE_FRAME = 5     /* 0/1 (default 1): shallow scenes render a frame in one cooperative launch */
 };
 

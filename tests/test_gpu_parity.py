@@ -47,7 +47,8 @@ def assert_hits_identical(a, b):
         assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
 
 
-# kernel schedules (XNART_OPT_TRAVERSAL): 1 = one thread per ray, 2 = one octet (8 lanes) per ray
+# kernel schedules (XNART_OPT_TRAVERSAL): 1 = one thread per ray, 2 = wavefront (persistent trace kernel; scenes
+# whose OctreeSpatialManager tree has internal nodes — "many" — fall back to 1)
 SCHEDULES = [1, 2]
 
 

@@ -18,6 +18,16 @@
 //            smallest position.  Mesh trees store mesh-relative triangle indices, the scene tree
 //            stores object ids.
 //
+// Internal nodes of the MESH trees additionally get a 128-byte expansion record (one cache line,
+// 8 x float4), indexed like consMax[]:
+//   inner[8k+0] = x planes (lo0, hi0, lo1, hi1)   child (i,j,k) = 4i+2j+k spans x in [lo_i, hi_i]: the 8
+//   inner[8k+1] = y planes (lo0, hi0, lo1, hi1)   children of a node are built from two halves per axis
+//   inner[8k+2] = z planes (lo0, hi0, lo1, hi1)   (MeshOctree.cs:207-222), so 12 planes describe all 8 boxes
+//   inner[8k+3] = (consMax.xyz, 0)                and one expansion costs 12 sub + 12 mul instead of 48 + 48
+//   inner[8k+4..7] = 8 child descriptors (a, b):  leaf  (first position in refs[]/leafTri, count >= 0)
+//                                                 inner (index of its own record, -1)
+//   The node's own Min is (x.lo0, y.lo0, z.lo0): child 0 starts at Min + size*0.
+//
 // Triangles (Triangle.cs:14-25) are split into a 64-byte intersection record and an 80-byte
 // shading record, both arrays of float4 read with 128-bit loads.
 //   leafTri[4p+0] = (n.xyz, bits(triangle index))  [4p+1] = (v1.xyz, 0)  [4p+2] = (E1.xyz, 0)  [4p+3] = (E2.xyz, 0)
@@ -45,6 +55,8 @@ constexpr int kBuilderDepthGuard = 64;  // same guard as the oracle: deeper -> X
 
 struct DevMesh {
     float box[6];        // Mesh.MeshBoundingBox (Mesh.cs:34-39 prefilter)
+    float rootBox[6];    // bounds of the MeshOctree root (tight box, MeshOctree.cs:59-80)
+    int rootA, rootB;    // root descriptor: leaf (first ref, count) or inner (record index, -1)
     int rootNode;        // global node index of the MeshOctree root
     int triBase;         // first triangle of this mesh in triS
     float reflectiveness;
@@ -53,8 +65,9 @@ struct DevMesh {
     int flags;           // bit0 useTexture, bit1 interpolateNormals, bit2 transparent
     int texOffset;       // first texel in texels[]
     int texW, texH;
-    int _pad;
+    int _pad[9];         // 128 bytes
 };
+static_assert(sizeof(DevMesh) == 128, "DevMesh layout");
 enum { MESH_USE_TEXTURE = 1, MESH_INTERP_NORMALS = 2, MESH_TRANSPARENT = 4 };
 
 struct DevObj {
@@ -75,6 +88,7 @@ struct DevLight {
 struct DevScene {
     const float4* nodes;
     const float4* consMax;
+    const float4* inner;     // 8 x float4 per internal node of the mesh trees (expansion records)
     const int* refs;
     const float4* leafTri;
     const float4* triS;
@@ -82,8 +96,27 @@ struct DevScene {
     const DevObj* objs;
     const int* objMeshIds;
     const uint32_t* texels;
+    // (object, mesh) pairs in the reference's visiting order when the scene octree is a single leaf
+    // (<= itemTreshold objects, OctreeSpatialManager.cs:103): list order of the leaf, then mesh order
+    const int2* pairs;
+    int nPairs;          // 0 when the scene octree has internal nodes (wavefront path unavailable)
     int sceneRoot;
     int nMeshes, nObjs;
+};
+
+// Result of one top-level GetRayIntersection query, two 16-byte words per ray slot:
+//   out[2s]   = (object, mesh, triangle, position of the leaf reference), object = -1: miss
+//   out[2s+1] = (u, v, d, 0) as float bits
+// One batch of queries for the persistent trace kernel: nSeg segments of *segCount rays each,
+// segment q occupying slots [q*segStride, q*segStride + *segCount).
+struct TraceJob {
+    const float4* rayO;      // (origin.xyz, -)
+    const float4* rayD;      // (direction.xyz, -)
+    const int2* rayIgn;      // (mesh, triangle) identity of the origin triangle, (-1,-1) = none
+    int4* out;
+    const unsigned int* segCount;
+    unsigned int* fetch;     // work counter, zero at launch
+    unsigned int nSeg, segStride;
 };
 
 struct DevFrame {
@@ -96,7 +129,7 @@ struct DevFrame {
     // chunk of shard-local pixels handled by this launch sequence
     long long pixelBase;   // first shard-local pixel index of the chunk
     int chunkPixels;
-    int _pad;
+    int tiled;             // 1: shard-local pixel indices run over 8x4 tiles (kernels.cu: pixelOf)
 };
 
 // Per-render path arena (SoA over "path nodes": one node per traced primary/reflection/refraction ray).
@@ -116,6 +149,14 @@ struct DevArena {
     unsigned long long* counters;  // kCounterSlots
     unsigned int nodeCapacity, rayCapacity;
     unsigned int* overflow;
+    // wavefront path (deep scenes): closest hits of the level's rays, and the shadow-ray batch of the level
+    int4* hit;           // 2 per ray slot of the level
+    float4* shO;         // nLights segments of rayCapacity slots: (hit position, distance to the light)
+    float4* shD;
+    int2* shIgn;
+    int4* shHit;         // 2 per shadow slot
+    unsigned int* shadowHits;   // [maxLevels+2] hits per level (= rays per shadow segment)
+    unsigned int* fetch;        // [2*(maxLevels+2)] work counters of the trace launches
 };
 
 enum {

@@ -1,4 +1,5 @@
-// kernels.h — launch wrappers of the trace kernels (implemented in kernels.cu).
+// kernels.h — launch wrappers of the trace kernels (kernels.cu: one thread per ray; wavefront.cu:
+// persistent trace kernel + streaming shade kernels for deep octrees).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -8,11 +9,10 @@
 namespace xn {
 
 // One wave of the trace loop: closest hit + shadow rays + shading for every ray of `level`.
-// upperBound only sizes the grid (the real count is read on the device).  coop selects the octet
-// schedule (8 lanes walk one ray together) instead of one thread per ray; deep selects the
+// upperBound only sizes the grid (the real count is read on the device).  deep selects the
 // high-occupancy (64-register) build of the per-thread kernel.
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
-                        long long upperBound, int maxBlocks, bool count, bool coop, bool deep, cudaStream_t st);
+                        long long upperBound, int maxBlocks, bool count, bool deep, cudaStream_t st);
 
 // The whole frame (all levels + resolve) in one cooperative launch; `blocks` must not exceed
 // frameKernelMaxBlocks().  stamps = 3 x uint64 device words (global timer at the phase boundaries).
@@ -27,6 +27,20 @@ cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long 
 // Batch closest-hit queries (xnart_trace_rays).
 cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
-                            int maxBlocks, bool count, bool coop, cudaStream_t st);
+                            int maxBlocks, bool count, cudaStream_t st);
+
+// ---- wavefront path (wavefront.cu) ----------------------------------------------------------
+int traceKernelBlocksPerSm(bool count);   // resident blocks of the persistent trace kernel
+cudaError_t launchGenPrimary(const DevFrame& F, const DevArena& A, int maxBlocks, cudaStream_t st);
+// One batch of GetRayIntersection queries through the persistent kernel (`blocks` resident blocks).
+cudaError_t launchTrace(const DevScene& S, const TraceJob& J, unsigned long long* counters, int blocks, bool count, cudaStream_t st);
+cudaError_t launchShadeA(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
+                         long long upperBound, int maxBlocks, cudaStream_t st);
+cudaError_t launchShadeB(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
+                         long long upperBound, int maxBlocks, cudaStream_t st);
+cudaError_t launchPackRays(const float* rays6, const int* ignore2, long long n, float4* rayO, float4* rayD, int2* rayIgn,
+                           int maxBlocks, cudaStream_t st);
+cudaError_t launchUnpackHits(const DevScene& S, const int4* hit, long long n, int* objId, int* meshId, int* triId, float* u, float* v,
+                             float* d, float* pos3, unsigned long long* counters, int maxBlocks, cudaStream_t st);
 
 }  // namespace xn

@@ -90,229 +90,191 @@ struct MeshHit {
 
 struct StackEntry { int node; float t; };
 
-// ---------------------------------------------------------------------------------------------
-// MeshOctree.GetRayIntersection
-// ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-__device__ __forceinline__ bool traceMesh(const DevScene& S, int rootNode, int triBase, const RayPre& r, int ignoreTri,
-                                          MeshHit& out, Ctr& ctr) {
-    StackEntry stack[kMeshStack];
-    const float4* __restrict__ nodes = S.nodes;
-    float K = INFINITY;
-    bool found = false;
-    float bd = 0.0f, bu = 0.0f, bv = 0.0f;
-    int btri = -1, bkey = 0;
+// Mesh-walk stack entry: a child descriptor (see device_types.h, inner[8k+4..7]) and its entry distance.
+struct WalkEntry { int a, b; float t; };
 
-    float4 lo = __ldg(&nodes[2 * rootNode]), hi = __ldg(&nodes[2 * rootNode + 1]);
-    float t0;
-    if (COUNT) ctr.nBox++;
-    if (!slab(make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z), r, t0)) return false;
-    int sp = 0;
-    int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
-    float tcur = t0;
-    for (;;) {
-        if (w1 >= 0) {
-            // ---- leaf: every triangle of containingObjects (MeshOctree.cs:286-304)
-            bool lf = false;
-            float ld = FLT_MAX, lu = 0.0f, lv = 0.0f;
-            int lt = -1, lk = 0;
-            const float4* __restrict__ R = S.leafTri + 4 * (size_t)w0;
-            for (int i = 0; i < w1; i++) {
-                // all four loads of the record are issued together (one round trip); a back-facing
-                // triangle wastes three of them, which costs L1 bandwidth the kernel has to spare
-                const float4* __restrict__ T4 = R + 4 * (size_t)i;
-                float4 n4 = __ldg(&T4[0]), a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
-                const int ti = __float_as_int(n4.w);
-                if (COUNT) ctr.nTriRef++;
-                if (ti == ignoreTri) continue;  // ignoreTriangle != triangles[i] (reference identity)
-                // dot(surfaceNormal, D) > 0 -> back face (RayExtensions.cs:48-51)
-                if (dot(mk(n4.x, n4.y, n4.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; continue; }
-                if (COUNT) ctr.nTriFull++;
-                V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z);
-                V3 T = sub(r.o, mk(a.x, a.y, a.z));
-                V3 P = cross(r.d, E2);
-                V3 Q = cross(T, E1);
-                float row1 = dot(Q, E2), row2 = dot(P, T), row3 = dot(Q, r.d);
-                float inv = 1.0f / dot(P, E1);
-                float dist = inv * row1, uu = inv * row2, vv = inv * row3;
-                if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f && dist < ld) {
-                    ld = dist; lu = uu; lv = vv; lt = ti; lk = w0 + i; lf = true;
-                }
-            }
-            if (lf) {
-                if (!found || tcur < K) { found = true; K = tcur; bd = ld; bu = lu; bv = lv; btri = lt; bkey = lk; }
-                else if (tcur == K && (ld < bd || (ld == bd && lk < bkey))) { bd = ld; bu = lu; bv = lv; btri = lt; bkey = lk; }
-            }
-        } else {
-            // ---- internal: slab-test all 8 children (MeshOctree.cs:336-339), push the accepted ones
-            // farthest first so the nearest pops first
-            const int oct = r.oct;
-#pragma unroll
-            for (int i = 7; i >= 0; i--) {
-                int c = w0 + (i ^ oct);
-                float4 clo = __ldg(&nodes[2 * c]), chi = __ldg(&nodes[2 * c + 1]);
-                float tc;
-                if (COUNT) ctr.nBox++;
-                if (slab(make_float3(clo.x, clo.y, clo.z), make_float3(chi.x, chi.y, chi.z), r, tc)) {
-                    // a leaf entered after K can never matter; internal nodes are re-examined at pop
-                    // time against their conservative box
-                    if (!(tc > K) || __float_as_int(chi.w) < 0) {
-                        stack[sp].node = c; stack[sp].t = tc; sp++;
-                    }
-                }
-            }
-        }
-        // ---- pop the next node that survives the prune test
-        bool got = false;
-        while (sp > 0) {
-            sp--;
-            int n = stack[sp].node;
-            float tn = stack[sp].t;
-            int nw0 = __float_as_int(__ldg(&nodes[2 * n]).w);
-            float4 nhi = __ldg(&nodes[2 * n + 1]);
-            int nw1 = __float_as_int(nhi.w);
-            if (tn > K) {
-                if (nw1 >= 0) continue;  // leaf entered after K
-                // internal: entry distance on the conservative box (own Min, consMax)
-                float4 nlo = __ldg(&nodes[2 * n]);
-                float4 cm = __ldg(&S.consMax[-1 - nw1]);
-                float tcns;
-                bool h = slab(make_float3(nlo.x, nlo.y, nlo.z), make_float3(cm.x, cm.y, cm.z), r, tcns);
-                if (h && tcns > K) continue;
-            }
-            w0 = nw0; w1 = nw1; tcur = tn;
-            got = true;
-            break;
-        }
-        if (!got) break;
+#ifndef XN_LEAF_CHUNK
+#define XN_LEAF_CHUNK 12   // triangles tested per visit of the leaf phase (longer leaves are resumed)
+#endif
+#ifndef XN_DESCEND_MAX
+#define XN_DESCEND_MAX 4   // node expansions per visit of the descend phase
+#endif
+
+// State of one MeshOctree.GetRayIntersection walk (all scalars: lives in registers).
+struct Walk {
+    float K;            // entry distance of the nearest leaf that produced an accepted triangle
+    bool found;
+    float bd, bu, bv;   // best candidate of the current K group
+    int btri, bkey;
+    int ca, cb;         // held node: leaf (first ref, remaining count) or inner (record, -1)
+    float ct;           // its entry distance
+    bool have;
+    int sp;
+};
+
+// One triangle of a leaf: IntersectsTriangleBackfaceCulling (RayExtensions.cs:42-75) and the
+// closest-hit bookkeeping of MeshOctree.GetRayIntersection (MeshOctree.cs:286-304) restated per
+// triangle: an accepted triangle of a leaf entered at tcur < K opens a new group (older candidates
+// are void); at tcur == K the candidates merge by (distance, position) — positions increase inside
+// a leaf, so this equals "strict < keeps the first of equal distances" followed by the group merge.
+template <bool COUNT>
+__device__ __forceinline__ void testTriangle(const float4 n4, const float4 a, const float4 b, const float4 c, int pos, const RayPre& r,
+                                             int ignoreTri, Walk& w, Ctr& ctr) {
+    const int ti = __float_as_int(n4.w);
+    if (COUNT) ctr.nTriRef++;
+    if (ti == ignoreTri) return;  // ignoreTriangle != triangles[i] (reference identity)
+    // dot(surfaceNormal, D) > 0 -> back face (RayExtensions.cs:48-51)
+    if (dot(mk(n4.x, n4.y, n4.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; return; }
+    if (COUNT) ctr.nTriFull++;
+    V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z);
+    V3 T = sub(r.o, mk(a.x, a.y, a.z));
+    V3 P = cross(r.d, E2);
+    V3 Q = cross(T, E1);
+    float row1 = dot(Q, E2), row2 = dot(P, T), row3 = dot(Q, r.d);
+    float inv = 1.0f / dot(P, E1);
+    float dist = inv * row1, uu = inv * row2, vv = inv * row3;
+    if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f) {
+        if (!w.found || w.ct < w.K) { w.found = true; w.K = w.ct; w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
+        else if (dist < w.bd || (dist == w.bd && pos < w.bkey)) { w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
     }
-    out.tri = btri; out.key = bkey; out.u = bu; out.v = bv; out.d = bd;
-    return found;
 }
 
 // ---------------------------------------------------------------------------------------------
-// MeshOctree.GetRayIntersection, cooperative form: the 8 lanes of an octet walk ONE ray together.
+// MeshOctree.GetRayIntersection as two alternating steps.
 //
-// The per-thread walk above diverges badly on deep trees (on the 1M-triangle grid ncu shows ~9 of
-// 32 lanes active: one lane is in a 50-triangle leaf while its neighbours test child boxes).  Here
-// every step is uniform across the octet: an internal step slab-tests the node's 8 children at
-// once (lane j takes the child at front-to-back position j, i.e. child j ^ octant; the 8 x 32 B
-// child block is one contiguous 256-byte read), `ballot` yields the mask of accepted children, and
-// the walk keeps ONE entry per tree level (child block, pending mask, each lane's own entry
-// distance) instead of a stack of nodes; a leaf step tests 8 triangles at a time.  Same visiting
-// order, same K rule and same tie-break as the per-thread walk, so results and work counters are
-// identical; only the lane-level schedule differs.
+// walkDescend pops / expands internal nodes until the lane holds a leaf (at most XN_DESCEND_MAX
+// expansions per call); walkLeaf tests at most XN_LEAF_CHUNK triangles of the held leaf.  Callers
+// alternate the two, so the lanes of a warp run the same kind of work at the same time instead of
+// one lane grinding through a 50-triangle leaf while its neighbours expand nodes.
+// Expansion uses the node's 128-byte record: per axis the two child halves are two consecutive
+// slabs, so the 8 entry/exit distances come from 12 plane distances (computed once) and min/max.
+// The nearest accepted child stays in registers; the others go to the stack farthest first.
+// Visiting order, K rule, prune rule and tie-break are those of the oracle's pruned walk, so the
+// work counters agree with it exactly.
 // ---------------------------------------------------------------------------------------------
-typedef cg::thread_block_tile<8> Octet;
-constexpr int kMeshLevels = kMaxMeshDepth + 2;
-
 template <bool COUNT>
-__device__ __forceinline__ bool traceMeshOctet(const Octet& g, const DevScene& S, int rootNode, int triBase, const RayPre& r,
-                                               int ignoreTri, MeshHit& out, Ctr& ctr) {
-    const int lane = (int)g.thread_rank();
-    const float4* __restrict__ nodes = S.nodes;
-    float lvT[kMeshLevels];
-    int lvBase[kMeshLevels];
-    unsigned lvMask[kMeshLevels];
-    float K = INFINITY;
-    bool found = false;      // uniform
-    bool rv = false;         // this lane holds a candidate of the current K group
-    float bd = 0.0f, bu = 0.0f, bv = 0.0f;
-    int btri = -1, bkey = 0;
-
-    float4 lo = __ldg(&nodes[2 * rootNode]), hi = __ldg(&nodes[2 * rootNode + 1]);
+__device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const RayPre& r, Walk& w, Ctr& ctr) {
     float t0;
-    if (COUNT && lane == 0) ctr.nBox++;
-    if (!slab(make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z), r, t0)) return false;
-    int level = -1;
-    int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
-    float tcur = t0;
-    for (;;) {
-        if (w1 >= 0) {
-            // ---- leaf: 8 triangles per step; each lane keeps the best of the ones it tested
-            bool lf = false;
-            float ld = FLT_MAX, lu = 0.0f, lv = 0.0f;
-            int lt = -1, lk = 0;
-            const float4* __restrict__ R = S.leafTri + 4 * (size_t)w0;
-            for (int i = lane; i < w1; i += 8) {
-                const float4* __restrict__ T4 = R + 4 * (size_t)i;
-                float4 n4 = __ldg(&T4[0]), a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
-                const int ti = __float_as_int(n4.w);
-                if (COUNT) ctr.nTriRef++;
-                if (ti == ignoreTri) continue;
-                if (dot(mk(n4.x, n4.y, n4.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; continue; }
-                if (COUNT) ctr.nTriFull++;
-                V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z);
-                V3 T = sub(r.o, mk(a.x, a.y, a.z));
-                V3 P = cross(r.d, E2);
-                V3 Q = cross(T, E1);
-                float row1 = dot(Q, E2), row2 = dot(P, T), row3 = dot(Q, r.d);
-                float inv = 1.0f / dot(P, E1);
-                float dist = inv * row1, uu = inv * row2, vv = inv * row3;
-                // within a lane positions increase, so strict `<` keeps the earliest of equal distances
-                if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f && dist < ld) {
-                    ld = dist; lu = uu; lv = vv; lt = ti; lk = w0 + i; lf = true;
-                }
+    if (COUNT) ctr.nBox++;
+    if (!slab(make_float3(M->rootBox[0], M->rootBox[1], M->rootBox[2]), make_float3(M->rootBox[3], M->rootBox[4], M->rootBox[5]), r, t0))
+        return false;
+    w.K = INFINITY; w.found = false; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
+    w.ca = M->rootA; w.cb = M->rootB; w.ct = t0; w.have = true; w.sp = 0;
+    return true;
+}
+
+// Returns true when the walk is over (nothing held, stack empty).
+template <bool COUNT>
+__device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, Walk& w, WalkEntry* __restrict__ stack, Ctr& ctr) {
+    const bool ox = (r.oct & 4) != 0, oy = (r.oct & 2) != 0, oz = (r.oct & 1) != 0;
+#pragma unroll 1
+    for (int step = 0; step < XN_DESCEND_MAX; step++) {
+        if (!w.have) {
+            // pop the next entry that survives the cheap prune test
+            while (w.sp > 0) {
+                w.sp--;
+                const WalkEntry e = stack[w.sp];
+                if (e.b >= 0 && e.t > w.K) continue;  // leaf entered after K
+                w.ca = e.a; w.cb = e.b; w.ct = e.t; w.have = true;
+                break;
             }
-            if (g.any(lf)) {
-                if (!found || tcur < K) {  // this leaf opens a nearer group: older candidates are void
-                    found = true; K = tcur;
-                    rv = lf; bd = ld; bu = lu; bv = lv; btri = lt; bkey = lk;
-                } else if (tcur == K && lf && (!rv || ld < bd || (ld == bd && lk < bkey))) {
-                    rv = true; bd = ld; bu = lu; bv = lv; btri = lt; bkey = lk;
+            if (!w.have) return true;
+        }
+        if (w.cb >= 0) return false;  // a leaf
+        // ---- internal node: slab-test all 8 children (MeshOctree.cs:336-339)
+        const float4* __restrict__ R = S.inner + 8 * (size_t)w.ca;
+        const float4 qx = __ldg(&R[0]), qy = __ldg(&R[1]), qz = __ldg(&R[2]);
+        const int2* __restrict__ D2 = reinterpret_cast<const int2*>(R + 4);
+        // descriptors in front-to-back position order: position p holds child p ^ octant
+        int2 ds[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) ds[p] = __ldg(&D2[p ^ r.oct]);
+        if (w.ct > w.K) {
+            // entered after K: prune on the conservative box (own Min, consMax)
+            const float4 qc = __ldg(&R[3]);
+            float tcns;
+            bool h = slab(make_float3(qx.x, qy.x, qz.x), make_float3(qc.x, qc.y, qc.z), r, tcns);
+            if (h && tcns > w.K) { w.have = false; continue; }
+        }
+        if (COUNT) ctr.nBox += 8;
+        w.have = false;
+        if (r.par == 0) {
+            // planes in the order the ray meets them: (lo0, hi0, lo1, hi1), reversed for a negative
+            // direction; (plane - origin) * inv is monotone in the plane, so near/far need no compare
+            const float x0 = ((ox ? qx.w : qx.x) - r.o.x) * r.inv.x, x1 = ((ox ? qx.z : qx.y) - r.o.x) * r.inv.x;
+            const float x2 = ((ox ? qx.y : qx.z) - r.o.x) * r.inv.x, x3 = ((ox ? qx.x : qx.w) - r.o.x) * r.inv.x;
+            const float y0 = ((oy ? qy.w : qy.x) - r.o.y) * r.inv.y, y1 = ((oy ? qy.z : qy.y) - r.o.y) * r.inv.y;
+            const float y2 = ((oy ? qy.y : qy.z) - r.o.y) * r.inv.y, y3 = ((oy ? qy.x : qy.w) - r.o.y) * r.inv.y;
+            const float z0 = ((oz ? qz.w : qz.x) - r.o.z) * r.inv.z, z1 = ((oz ? qz.z : qz.y) - r.o.z) * r.inv.z;
+            const float z2 = ((oz ? qz.y : qz.z) - r.o.z) * r.inv.z, z3 = ((oz ? qz.x : qz.w) - r.o.z) * r.inv.z;
+            // tmin = Max(tz, Max(ty, Max(tx, 0))), tmax = Min(tz', Min(ty', Min(tx', MaxValue))) in the
+            // framework's axis order; position p = 4*px + 2*py + pz (first/second half met per axis)
+            const float nx[2] = {fmaxf(x0, 0.0f), fmaxf(x2, 0.0f)}, fx[2] = {fminf(x1, FLT_MAX), fminf(x3, FLT_MAX)};
+            const float ny[2] = {y0, y2}, fy[2] = {y1, y3}, nz[2] = {z0, z2}, fz[2] = {z1, z3};
+#pragma unroll
+            for (int p = 7; p >= 0; p--) {
+                const int px = p >> 2, py = (p >> 1) & 1, pz = p & 1;
+                const float tmin = fmaxf(nz[pz], fmaxf(ny[py], nx[px]));
+                const float tmax = fminf(fz[pz], fminf(fy[py], fx[px]));
+                const int2 d = ds[p];
+                // empty leaves are dropped; a leaf entered after K can never matter; internal nodes are
+                // re-examined when popped (conservative box)
+                if (!(tmin > tmax) && d.y != 0 && (d.y < 0 || !(tmin > w.K))) {
+                    if (w.have) { stack[w.sp].a = w.ca; stack[w.sp].b = w.cb; stack[w.sp].t = w.ct; w.sp++; }
+                    w.ca = d.x; w.cb = d.y; w.ct = tmin; w.have = true;
                 }
             }
         } else {
-            // ---- internal: lane j tests the child at front-to-back position j
-            const int c = w0 + (lane ^ r.oct);
-            float4 clo = __ldg(&nodes[2 * c]), chi = __ldg(&nodes[2 * c + 1]);
-            float tc;
-            if (COUNT) ctr.nBox++;
-            bool keep = slab(make_float3(clo.x, clo.y, clo.z), make_float3(chi.x, chi.y, chi.z), r, tc);
-            keep = keep && (!(tc > K) || __float_as_int(chi.w) < 0);
-            unsigned mask = g.ballot(keep);
-            if (mask) { level++; lvT[level] = tc; lvBase[level] = w0; lvMask[level] = mask; }
-        }
-        // ---- next node: nearest pending child of the deepest level that still has one
-        bool got = false;
-        while (level >= 0) {
-            unsigned mask = lvMask[level];
-            if (!mask) { level--; continue; }
-            const int j = __ffs((int)mask) - 1;
-            lvMask[level] = mask & (mask - 1u);
-            const float tn = g.shfl(lvT[level], j);
-            const int n = lvBase[level] + (j ^ r.oct);
-            float4 nlo = __ldg(&nodes[2 * n]), nhi = __ldg(&nodes[2 * n + 1]);
-            const int nw1 = __float_as_int(nhi.w);
-            if (tn > K) {
-                if (nw1 >= 0) continue;
-                float4 cm = __ldg(&S.consMax[-1 - nw1]);
-                float tcns;
-                bool h = slab(make_float3(nlo.x, nlo.y, nlo.z), make_float3(cm.x, cm.y, cm.z), r, tcns);
-                if (h && tcns > K) continue;
-            }
-            w0 = __float_as_int(nlo.w); w1 = nw1; tcur = tn;
-            got = true;
-            break;
-        }
-        if (!got) break;
-    }
-    if (!found) return false;
-    // minimum (distance, position) over the lanes' candidates; every lane ends with the same winner
-    float d = rv ? bd : INFINITY;
-    int key = rv ? bkey : INT_MAX, src = lane;
+            // a direction component below 1e-6 takes the slab test's containment branch: general form
+            const float lx[2] = {qx.x, qx.z}, hx[2] = {qx.y, qx.w}, ly[2] = {qy.x, qy.z}, hy[2] = {qy.y, qy.w};
+            const float lz[2] = {qz.x, qz.z}, hz[2] = {qz.y, qz.w};
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        float d2 = g.shfl_xor(d, o);
-        int k2 = g.shfl_xor(key, o), s2 = g.shfl_xor(src, o);
-        if (d2 < d || (d2 == d && k2 < key)) { d = d2; key = k2; src = s2; }
+            for (int p = 7; p >= 0; p--) {
+                const int c = p ^ r.oct;
+                const int i = c >> 2, j = (c >> 1) & 1, k = c & 1;
+                float tc;
+                const bool h = slab(make_float3(i ? lx[1] : lx[0], j ? ly[1] : ly[0], k ? lz[1] : lz[0]),
+                                    make_float3(i ? hx[1] : hx[0], j ? hy[1] : hy[0], k ? hz[1] : hz[0]), r, tc);
+                const int2 d = ds[p];
+                if (h && d.y != 0 && (d.y < 0 || !(tc > w.K))) {
+                    if (w.have) { stack[w.sp].a = w.ca; stack[w.sp].b = w.cb; stack[w.sp].t = w.ct; w.sp++; }
+                    w.ca = d.x; w.cb = d.y; w.ct = tc; w.have = true;
+                }
+            }
+        }
     }
-    out.d = d;
-    out.key = key;
-    out.u = g.shfl(bu, src);
-    out.v = g.shfl(bv, src);
-    out.tri = g.shfl(btri, src);
-    return true;
+    return false;
+}
+
+// Up to XN_LEAF_CHUNK triangles of the held leaf's containingObjects (MeshOctree.cs:286-304).
+template <bool COUNT>
+__device__ __forceinline__ void walkLeaf(const DevScene& S, const RayPre& r, int ignoreTri, Walk& w, Ctr& ctr) {
+    if (!(w.have && w.cb >= 0)) return;
+    const int n = min(w.cb, XN_LEAF_CHUNK);
+    const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)w.ca;
+#pragma unroll 1
+    for (int i = 0; i < n; i++, T4 += 4) {
+        // all four loads of the record are issued together (one round trip)
+        const float4 n4 = __ldg(&T4[0]), a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
+        testTriangle<COUNT>(n4, a, b, c, w.ca + i, r, ignoreTri, w, ctr);
+    }
+    w.ca += n; w.cb -= n;
+    if (w.cb == 0) w.have = false;
+}
+
+// One thread, one ray: the whole walk.
+template <bool COUNT>
+__device__ __forceinline__ bool traceMesh(const DevScene& S, const DevMesh* __restrict__ M, const RayPre& r, int ignoreTri,
+                                          MeshHit& out, Ctr& ctr) {
+    WalkEntry stack[kMeshStack];
+    Walk w;
+    if (!walkStart<COUNT>(M, r, w, ctr)) return false;
+    for (;;) {
+        if (walkDescend<COUNT>(S, r, w, stack, ctr)) break;
+        walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+    }
+    out.tri = w.btri; out.key = w.bkey; out.u = w.bu; out.v = w.bv; out.d = w.bd;
+    return w.found;
 }
 
 struct Hit {
@@ -323,10 +285,8 @@ struct Hit {
 };
 
 // Per-object block of OctreeSpatialManager.GetRayIntersection (OctreeSpatialManager.cs:347-428).
-// COOP: called by all 8 lanes of an octet with identical arguments; everything but the mesh walk
-// is computed redundantly (and counted once).
-template <bool COUNT, bool COOP>
-__device__ __forceinline__ void objectQuery(const Octet& g, const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
+template <bool COUNT>
+__device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
                                             float& minDistance, bool& found, Hit& best, Ctr& ctr) {
     const DevObj* __restrict__ O = &S.objs[objIdx];
     // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (:358-364)
@@ -341,13 +301,12 @@ __device__ __forceinline__ void objectQuery(const Octet& g, const DevScene& S, i
         int meshId = __ldg(&S.objMeshIds[ms + mi]);
         const DevMesh* __restrict__ M = &S.meshes[meshId];
         float tb;
-        if (COUNT && (!COOP || g.thread_rank() == 0)) ctr.nBox++;
+        if (COUNT) ctr.nBox++;
         // Mesh.RayIntersects (Mesh.cs:34-39)
         if (!slab(make_float3(M->box[0], M->box[1], M->box[2]), make_float3(M->box[3], M->box[4], M->box[5]), r, tb)) continue;
         MeshHit mh;
         int ign = (ignMesh == meshId) ? ignTri : -1;
-        const bool ok = COOP ? traceMeshOctet<COUNT>(g, S, M->rootNode, M->triBase, r, ign, mh, ctr)
-                             : traceMesh<COUNT>(S, M->rootNode, M->triBase, r, ign, mh, ctr);
+        const bool ok = traceMesh<COUNT>(S, M, r, ign, mh, ctr);
         if (ok && mh.d < minDistance) {
             minDistance = mh.d;
             best.obj = objIdx; best.mesh = meshId; best.tri = mh.tri; best.key = mh.key;
@@ -361,10 +320,10 @@ __device__ __forceinline__ void objectQuery(const Octet& g, const DevScene& S, i
 // OctreeSpatialManager.GetRayIntersection.  Same group/early-exit semantics one level up; with
 // <= itemTreshold (20) objects the tree is the root leaf alone.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT, bool COOP>
-__device__ __forceinline__ bool traceSceneT(const Octet& g, const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
+template <bool COUNT>
+__device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
     if (!finite3(ro) || !finite3(rd)) return false;
-    const bool cnt = COUNT && (!COOP || g.thread_rank() == 0);  // uniform work is counted once per octet
+    const bool cnt = COUNT;
     const float4* __restrict__ nodes = S.nodes;
     RayPre r = prepRay(ro, rd);
     float4 lo = __ldg(&nodes[2 * S.sceneRoot]), hi = __ldg(&nodes[2 * S.sceneRoot + 1]);
@@ -393,7 +352,7 @@ __device__ __forceinline__ bool traceSceneT(const Octet& g, const DevScene& S, V
             for (int i = 0; i < w1; i++) {
                 const float before = ld;
                 const bool fb = lf;
-                objectQuery<COUNT, COOP>(g, S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
+                objectQuery<COUNT>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
                 if (lf && (!fb || ld < before)) lkey = w0 + i;
             }
             if (lf) {
@@ -443,34 +402,6 @@ __device__ __forceinline__ bool traceSceneT(const Octet& g, const DevScene& S, V
         out = best;
     }
     return found;
-}
-
-// One thread, one ray.
-template <bool COUNT>
-__device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
-    const Octet g = cg::tiled_partition<8>(cg::this_thread_block());
-    return traceSceneT<COUNT, false>(g, S, ro, rd, ignMesh, ignTri, out, ctr);
-}
-
-// Every lane of the octet brings (at most) one ray; the octet walks them one after the other, all
-// 8 lanes working on the same ray.  Must be called by all 8 lanes together; `want` says whether
-// this lane has a ray.  Returns this lane's own result.
-template <bool COUNT>
-__device__ __forceinline__ bool traceSceneCoop(const Octet& g, const DevScene& S, bool want, V3 ro, V3 rd, int ignMesh,
-                                               int ignTri, Hit& out, Ctr& ctr) {
-    unsigned pending = g.ballot(want);
-    bool myOk = false;
-    while (pending) {
-        const int src = __ffs((int)pending) - 1;
-        pending &= pending - 1u;
-        V3 o = mk(g.shfl(ro.x, src), g.shfl(ro.y, src), g.shfl(ro.z, src));
-        V3 d = mk(g.shfl(rd.x, src), g.shfl(rd.y, src), g.shfl(rd.z, src));
-        const int im = g.shfl(ignMesh, src), it = g.shfl(ignTri, src);
-        Hit h;
-        const bool ok = traceSceneT<COUNT, true>(g, S, o, d, im, it, h, ctr);
-        if ((int)g.thread_rank() == src) { myOk = ok; if (ok) out = h; }
-    }
-    return myOk;
 }
 
 // ---------------------------------------------------------------------------------------------

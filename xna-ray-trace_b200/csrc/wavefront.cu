@@ -1,0 +1,360 @@
+// wavefront.cu — the trace loop for scenes with deep MeshOctrees (hand-written CUDA, sm_100a).
+//
+// The cost of one GetRayIntersection query on a deep octree is heavy-tailed: most rays touch a
+// few leaves, some graze the surface through hundreds.  With one thread per ray and a whole
+// CastRay per thread (kernels.cu) the stragglers hold their warps hostage — ncu on the
+// 1M-triangle grid shows 5 of 32 lanes active (profiles/r01c).  Here the recursion level is split
+// into its queries and every query batch runs through ONE persistent kernel in which a lane that
+// finishes its ray immediately takes the next one from the batch:
+//
+//   level L:  k_gen_primary (L = 0)      RayTracer.Render's Unproject pair (RayTracer.cs:410-421) -> ray queue
+//             k_trace      (level rays)  OctreeSpatialManager / MeshOctree.GetRayIntersection (RayTracer.cs:512)
+//             k_shade_a                  hit position, fragment normal (:520-531), shadow rays (:467-482)
+//             k_trace      (shadow rays) IsLightPathObstructed's query (:485), nLights segments
+//             k_shade_b                  light sum (:535-542), surface colour, reflection / refraction rays of
+//                                        level L+1 (:545-702), path node
+//   then k_resolve (kernels.cu) bottom-up, as in the per-thread path.
+//
+// k_trace: persistent warps; per lane a small state machine (idle -> pick the next (object, mesh)
+// pair -> walk its octree, alternating descend and leaf steps (trace.cuh) -> merge -> next pair ->
+// write the hit).  All 32 lanes stay in the outer loop until the batch is drained, so the phases
+// reconverge at __syncwarp() and idle lanes refill from the batch through one warp-aggregated
+// atomicAdd.  Per-ray results do not depend on which lane or when a ray is traced, so frames stay
+// bit-identical to the per-thread path and to the oracle.
+//
+// Available when the scene octree is a single leaf (<= itemTreshold objects: every BASELINE
+// configuration); scenes with a deeper OctreeSpatialManager tree use the per-thread kernels.
+#include "kernels.h"
+#include "shade.cuh"
+
+#ifndef XN_TRACE_MIN_BLOCKS
+#define XN_TRACE_MIN_BLOCKS 4
+#endif
+
+namespace xn {
+
+// ---------------------------------------------------------------------------------------------
+// level 0: primary rays into the queue (tile order, see pixelOf)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gen_primary(DevFrame F, DevArena A) {
+    const unsigned count = (unsigned)F.chunkPixels;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { A.levelCount[0] = count; A.levelBase[0] = 0u; }
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        const RayIn r = loadRay(F, A, 0, idx);
+        A.rayO[0][idx] = make_float4(r.o.x, r.o.y, r.o.z, r.refIndex);
+        A.rayD[0][idx] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+        A.rayIgn[0][idx] = make_int2(-1, -1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent trace kernel
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, TraceJob J, unsigned long long* __restrict__ counters) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned segCount = *J.segCount;
+    const unsigned total = segCount * J.nSeg;
+    WalkEntry stack[kMeshStack];
+    Ctr ctr;
+    ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
+
+    int slot = -1;            // ray slot this lane owns, -1 = idle
+    int pi = 0;               // (object, mesh) pair being tried / walked
+    bool walking = false;
+    bool exhausted = false;   // warp-uniform: the batch has no more rays to hand out
+    V3 wo = mk(0.0f, 0.0f, 0.0f), wd = wo;  // world-space ray
+    int ignM = -1, ignT = -1;
+    RayPre r;                 // object-space ray of the pair being walked
+    r.o = r.d = r.inv = wo; r.par = r.oct = 0;
+    int ignoreTri = -1;
+    Walk w;
+    w.K = INFINITY; w.found = false; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
+    w.ca = w.cb = 0; w.ct = 0.0f; w.have = false; w.sp = 0;
+    // best hit over the pairs tried so far (OctreeSpatialManager.cs:371-377: strict <, first wins)
+    float bestD = FLT_MAX, bestU = 0.0f, bestV = 0.0f;
+    int bestPair = -1, bestTri = -1, bestKey = 0;
+
+    const float4 slo = __ldg(&S.nodes[2 * S.sceneRoot]), shi = __ldg(&S.nodes[2 * S.sceneRoot + 1]);
+
+    for (;;) {
+        // ---- FETCH: idle lanes take the next rays of the batch
+        const unsigned idleMask = __ballot_sync(FULL, slot < 0);
+        if (idleMask != 0u && !exhausted) {
+            const unsigned n = (unsigned)__popc(idleMask);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(J.fetch, n);
+            base = __shfl_sync(FULL, base, 0);
+            if (slot < 0) {
+                const unsigned i = base + (unsigned)__popc(idleMask & ((1u << lane) - 1u));
+                if (i < total) {
+                    unsigned q = 0, h = i;
+                    if (J.nSeg > 1) { q = i / segCount; h = i - q * segCount; }
+                    slot = (int)(q * J.segStride + h);
+                    const float4 o4 = J.rayO[slot], d4 = J.rayD[slot];
+                    const int2 ig = J.rayIgn[slot];
+                    wo = mk(o4.x, o4.y, o4.z); wd = mk(d4.x, d4.y, d4.z);
+                    ignM = ig.x; ignT = ig.y;
+                    pi = 0; walking = false;
+                    bestD = FLT_MAX; bestPair = -1;
+                    // a non-finite ray fails every triangle test; the scene root must be hit
+                    // (OctreeSpatialManager.cs:457-461)
+                    bool ok = finite3(wo) && finite3(wd);
+                    if (ok) {
+                        const RayPre rw = prepRay(wo, wd);
+                        float t0;
+                        if (COUNT) ctr.nBox++;
+                        ok = slab(make_float3(slo.x, slo.y, slo.z), make_float3(shi.x, shi.y, shi.z), rw, t0);
+                    }
+                    if (!ok) pi = S.nPairs;
+                }
+            }
+            exhausted = base + n >= total;
+        }
+        if (__all_sync(FULL, slot < 0)) break;
+
+        // ---- SETUP: lanes between walks pick their next (object, mesh) pair, or finish the ray
+        if (slot >= 0 && !walking) {
+            while (pi < S.nPairs) {
+                const int2 pr = __ldg(&S.pairs[pi]);
+                const DevObj* __restrict__ O = &S.objs[pr.x];
+                // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (OctreeSpatialManager.cs:358-364)
+                const V3 v1 = transform43(wo, O->inv);
+                const V3 v2 = transform43(add(wo, wd), O->inv);
+                const V3 dd = normalize(sub(v2, v1));
+                if (!finite3(v1) || !finite3(dd)) { pi++; continue; }
+                r = prepRay(v1, dd);
+                const DevMesh* __restrict__ M = &S.meshes[pr.y];
+                float tb;
+                if (COUNT) ctr.nBox++;
+                // Mesh.RayIntersects (Mesh.cs:34-39)
+                if (!slab(make_float3(M->box[0], M->box[1], M->box[2]), make_float3(M->box[3], M->box[4], M->box[5]), r, tb)) { pi++; continue; }
+                ignoreTri = (ignM == pr.y) ? ignT : -1;
+                if (!walkStart<COUNT>(M, r, w, ctr)) { pi++; continue; }
+                walking = true;
+                break;
+            }
+            if (!walking) {
+                // every pair tried: the ray is finished
+                int4 a = make_int4(-1, -1, -1, 0), b = make_int4(0, 0, 0, 0);
+                if (bestPair >= 0) {
+                    const int2 pr = __ldg(&S.pairs[bestPair]);
+                    a = make_int4(pr.x, pr.y, bestTri, bestKey);
+                    b = make_int4(__float_as_int(bestU), __float_as_int(bestV), __float_as_int(bestD), 1);
+                }
+                J.out[2 * (size_t)slot] = a;
+                J.out[2 * (size_t)slot + 1] = b;
+                slot = -1;
+            }
+        }
+        __syncwarp();
+
+        // ---- DESCEND, then LEAF
+        bool over = false;
+        if (walking) over = walkDescend<COUNT>(S, r, w, stack, ctr);
+        __syncwarp();
+        if (walking && !over) walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+        __syncwarp();
+        if (walking && over) {
+            // minDistance bookkeeping of the object loop (OctreeSpatialManager.cs:370-377)
+            if (w.found && w.bd < bestD) { bestD = w.bd; bestU = w.bu; bestV = w.bv; bestTri = w.btri; bestKey = w.bkey; bestPair = pi; }
+            pi++;
+            walking = false;
+        }
+    }
+
+    if (COUNT) {
+        unsigned a = warpSum(ctr.nBox), b = warpSum(ctr.nTriRef), c = warpSum(ctr.nTriCulled), d = warpSum(ctr.nTriFull);
+        if (lane == 0) {
+            atomicAdd(&counters[CTR_NBOX], (unsigned long long)a);
+            atomicAdd(&counters[CTR_NTRIREF], (unsigned long long)b);
+            atomicAdd(&counters[CTR_NTRICULLED], (unsigned long long)c);
+            atomicAdd(&counters[CTR_NTRIFULL], (unsigned long long)d);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shade A: closest hits of the level -> hit position, fragment normal, shadow rays
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ Hit hitOf(const DevScene& S, const int4 a, const int4 b) {
+    Hit h;
+    h.obj = a.x; h.mesh = a.y; h.tri = a.z; h.key = a.w;
+    h.u = __int_as_float(b.x); h.v = __int_as_float(b.y); h.d = __int_as_float(b.z);
+    h.pos = mk(0.0f, 0.0f, 0.0f);
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+    const unsigned count = A.levelCount[level];
+    const unsigned base = A.levelBase[level];
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.levelBase[level + 1] = base + count;
+    unsigned nHits = 0;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        const unsigned node = base + idx;
+        const int4 ha = A.hit[2 * (size_t)idx], hb = A.hit[2 * (size_t)idx + 1];
+        if (ha.x < 0) {
+            A.color[node] = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);  // RayTracer.cs:732
+            A.flags[node] = 0u;
+            continue;
+        }
+        nHits++;
+        Hit h = hitOf(S, ha, hb);
+        // objectSpacePosition = v1 + (v2-v1)*u + (v3-v1)*v (MeshOctree.cs:310-312); world = Po * World (:441-443)
+        const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)h.key;
+        const float4 a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
+        const V3 po = add(add(mk(a.x, a.y, a.z), mul(mk(b.x, b.y, b.z), h.u)), mul(mk(c.x, c.y, c.z), h.v));
+        h.pos = transform43(po, S.objs[h.obj].world);
+        const DevMesh* __restrict__ M = &S.meshes[h.mesh];
+        const V3 N = fragmentNormal(S, M, M->triBase + h.tri, h);
+        // compact hit index: the shadow rays of hit k sit at slot q*rayCapacity + k, one segment per light
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned b0 = 0;
+        if (g.thread_rank() == 0) b0 = atomicAdd(&A.shadowHits[level], g.size());
+        const unsigned k = g.shfl(b0, 0) + g.thread_rank();
+        for (int q = 0; q < F.nLights; q++) {
+            float distToLight;
+            const V3 sd = shadowDir(lights[q], h.pos, distToLight);
+            const size_t s = (size_t)q * A.rayCapacity + k;
+            A.shO[s] = make_float4(h.pos.x, h.pos.y, h.pos.z, distToLight);
+            A.shD[s] = make_float4(sd.x, sd.y, sd.z, 0.0f);
+            A.shIgn[s] = make_int2(h.mesh, h.tri);
+        }
+        A.nodeA[node] = make_float4(h.pos.x, h.pos.y, h.pos.z, __uint_as_float(k));
+        A.nodeB[node] = make_float4(N.x, N.y, N.z, 0.0f);
+    }
+    const unsigned sH = warpSum(nHits);
+    if ((threadIdx.x & 31u) == 0 && sH) atomicAdd(&A.counters[CTR_HITS], (unsigned long long)sH);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shade B: shadow verdicts -> light sum, surface colour, next-level rays, path node
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shade_b(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+    const unsigned count = A.levelCount[level];
+    const unsigned base = A.levelBase[level];
+    const unsigned nextBase = base + count;
+    const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
+    const int in = level & 1;
+    unsigned nRefl = 0, nRefr = 0;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        const unsigned node = base + idx;
+        const int4 ha = A.hit[2 * (size_t)idx], hb = A.hit[2 * (size_t)idx + 1];
+        if (ha.x < 0) continue;
+        Hit h = hitOf(S, ha, hb);
+        const float4 pa = A.nodeA[node], nb = A.nodeB[node];
+        h.pos = mk(pa.x, pa.y, pa.z);
+        const unsigned k = __float_as_uint(pa.w);
+        const V3 N = mk(nb.x, nb.y, nb.z);
+        V3 lightResult = mk(0.0f, 0.0f, 0.0f);
+        for (int q = 0; q < F.nLights; q++) {
+            const size_t s = (size_t)q * A.rayCapacity + k;
+            const int4 sa = A.shHit[2 * s], sb = A.shHit[2 * s + 1];
+            const Hit sh = hitOf(S, sa, sb);
+            lightResult = addLight(S, lights[q], sa.x >= 0, sh, A.shO[s].w, h.pos, N, lightResult);
+        }
+        const DevMesh* __restrict__ M = &S.meshes[h.mesh];
+        const float4 o4 = A.rayO[in][idx], d4 = A.rayD[in][idx];
+        finishHit(S, F, A, level, last, node, nextBase, h, M, M->triBase + h.tri, N, lightResult, mk(d4.x, d4.y, d4.z), o4.w, nRefl, nRefr);
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned sR = warpSum(nRefl), sF = warpSum(nRefr);
+    if (lane == 0) {
+        if (sR) atomicAdd(&A.counters[CTR_RAYS_REFLECTION], (unsigned long long)sR);
+        if (sF) atomicAdd(&A.counters[CTR_RAYS_REFRACTION], (unsigned long long)sF);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch API (xnart_trace_rays): user rays -> queue layout, hits -> user arrays
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_rays(const float* __restrict__ rays6, const int* __restrict__ ignore2, long long n,
+                                                   float4* __restrict__ rayO, float4* __restrict__ rayD, int2* __restrict__ rayIgn) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        rayO[i] = make_float4(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2], 1.0f);
+        rayD[i] = make_float4(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5], 0.0f);
+        rayIgn[i] = ignore2 ? make_int2(ignore2[2 * i], ignore2[2 * i + 1]) : make_int2(-1, -1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unpack_hits(DevScene S, const int4* __restrict__ hit, long long n, int* __restrict__ objId,
+                                                     int* __restrict__ meshId, int* __restrict__ triId, float* __restrict__ u,
+                                                     float* __restrict__ v, float* __restrict__ d, float* __restrict__ pos3,
+                                                     unsigned long long* __restrict__ counters) {
+    unsigned nHits = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int4 ha = hit[2 * i], hb = hit[2 * i + 1];
+        const bool ok = ha.x >= 0;
+        if (ok) nHits++;
+        objId[i] = ok ? ha.x : -1; meshId[i] = ok ? ha.y : -1; triId[i] = ok ? ha.z : -1;
+        u[i] = ok ? __int_as_float(hb.x) : 0.0f; v[i] = ok ? __int_as_float(hb.y) : 0.0f; d[i] = ok ? __int_as_float(hb.z) : 0.0f;
+        if (pos3) {
+            V3 p = mk(0.0f, 0.0f, 0.0f);
+            if (ok) {
+                const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)ha.w;
+                const float4 a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
+                const V3 po = add(add(mk(a.x, a.y, a.z), mul(mk(b.x, b.y, b.z), __int_as_float(hb.x))), mul(mk(c.x, c.y, c.z), __int_as_float(hb.y)));
+                p = transform43(po, S.objs[ha.x].world);
+            }
+            pos3[3 * i] = p.x; pos3[3 * i + 1] = p.y; pos3[3 * i + 2] = p.z;
+        }
+    }
+    const unsigned sH = warpSum(nHits);
+    if ((threadIdx.x & 31u) == 0 && sH) atomicAdd(&counters[CTR_HITS], (unsigned long long)sH);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------
+static inline int gridFor(long long n, int maxBlocks) {
+    long long b = (n + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > maxBlocks) b = maxBlocks;
+    return (int)b;
+}
+
+int traceKernelBlocksPerSm(bool count) {
+    int perSm = 0;
+    cudaError_t e = count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true>, 256, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false>, 256, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return perSm;
+}
+
+cudaError_t launchGenPrimary(const DevFrame& F, const DevArena& A, int maxBlocks, cudaStream_t st) {
+    k_gen_primary<<<gridFor(F.chunkPixels, maxBlocks), 256, 0, st>>>(F, A);
+    return cudaGetLastError();
+}
+
+cudaError_t launchTrace(const DevScene& S, const TraceJob& J, unsigned long long* counters, int blocks, bool count, cudaStream_t st) {
+    if (count) k_trace<true><<<blocks, 256, 0, st>>>(S, J, counters);
+    else k_trace<false><<<blocks, 256, 0, st>>>(S, J, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launchShadeA(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
+                         long long upperBound, int maxBlocks, cudaStream_t st) {
+    k_shade_a<<<gridFor(upperBound, maxBlocks), 256, 0, st>>>(S, F, A, lights, level);
+    return cudaGetLastError();
+}
+
+cudaError_t launchShadeB(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
+                         long long upperBound, int maxBlocks, cudaStream_t st) {
+    k_shade_b<<<gridFor(upperBound, maxBlocks), 256, 0, st>>>(S, F, A, lights, level);
+    return cudaGetLastError();
+}
+
+cudaError_t launchPackRays(const float* rays6, const int* ignore2, long long n, float4* rayO, float4* rayD, int2* rayIgn,
+                           int maxBlocks, cudaStream_t st) {
+    k_pack_rays<<<gridFor(n, maxBlocks), 256, 0, st>>>(rays6, ignore2, n, rayO, rayD, rayIgn);
+    return cudaGetLastError();
+}
+
+cudaError_t launchUnpackHits(const DevScene& S, const int4* hit, long long n, int* objId, int* meshId, int* triId, float* u, float* v,
+                             float* d, float* pos3, unsigned long long* counters, int maxBlocks, cudaStream_t st) {
+    k_unpack_hits<<<gridFor(n, maxBlocks), 256, 0, st>>>(S, hit, n, objId, meshId, triId, u, v, d, pos3, counters);
+    return cudaGetLastError();
+}
+
+}  // namespace xn

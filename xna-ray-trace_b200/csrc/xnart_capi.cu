@@ -27,7 +27,7 @@ struct DeviceState {
     int smCount = 0;
     cudaStream_t stream = nullptr;
     // scene
-    float4* nodes = nullptr; float4* consMax = nullptr; int* refs = nullptr;
+    float4* nodes = nullptr; float4* consMax = nullptr; float4* inner = nullptr; int* refs = nullptr;
     float4* leafTri = nullptr; float4* triS = nullptr;
     DevMesh* meshes = nullptr; DevObj* objs = nullptr; int* objMeshIds = nullptr; uint32_t* texels = nullptr;
     DevLight* lights = nullptr; int nLightsUploaded = -1;
@@ -40,6 +40,9 @@ struct DeviceState {
     unsigned long long* counters = nullptr;
     unsigned long long* stamps = nullptr;   // k_frame: global timer at start / levels done / resolve done
     int frameBlocks = 0, frameBlocksCount = 0;  // resident grid of the cooperative frame kernel
+    int traceBlocks = 0, traceBlocksCount = 0;  // resident grid of the persistent trace kernel
+    int2* pairs = nullptr;
+    bool lastWave = false;
     bool lastFused = false;
     // output
     uint32_t* frameBuf = nullptr; size_t frameBufPixels = 0;
@@ -57,6 +60,8 @@ struct DeviceState {
 };
 
 constexpr int kMaxLevels = 30;
+// levelCount | levelBase | overflow(2) | shadowHits | fetch(2 per level)
+constexpr int kLevelWords = 5 * (kMaxLevels + 2) + 2;
 
 inline float __int_as_float_host(int v) {
     float f;
@@ -84,6 +89,7 @@ struct XnartCtx {
     bool fuseFrame = true;   // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
+    int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
     std::atomic<int64_t> launches{0};
     XnartCounters last{};
 };
@@ -107,9 +113,9 @@ static int fail(XnartCtx* c, int code, const std::string& msg) {
 
 static void freeScene(DeviceState& d) {
     cudaSetDevice(d.dev);
-    cudaFree(d.nodes); cudaFree(d.consMax); cudaFree(d.refs); cudaFree(d.leafTri); cudaFree(d.triS);
+    cudaFree(d.nodes); cudaFree(d.consMax); cudaFree(d.inner); cudaFree(d.pairs); cudaFree(d.refs); cudaFree(d.leafTri); cudaFree(d.triS);
     cudaFree(d.meshes); cudaFree(d.objs); cudaFree(d.objMeshIds); cudaFree(d.texels);
-    d.nodes = d.consMax = d.leafTri = d.triS = nullptr; d.refs = nullptr; d.meshes = nullptr; d.objs = nullptr;
+    d.nodes = d.consMax = d.inner = d.leafTri = d.triS = nullptr; d.pairs = nullptr; d.refs = nullptr; d.meshes = nullptr; d.objs = nullptr;
     d.objMeshIds = nullptr; d.texels = nullptr;
 }
 
@@ -157,12 +163,13 @@ int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds)
                 cudaEventCreateWithFlags(&d.evRendered[k], cudaEventDisableTiming);
                 cudaEventCreateWithFlags(&d.evCopied[k], cudaEventDisableTiming);
             }
-            cudaMalloc(&d.levelWords, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2));
+            cudaMalloc(&d.levelWords, sizeof(unsigned) * kLevelWords);
             cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounterSlots);
             cudaMalloc(&d.stamps, sizeof(unsigned long long) * 4);
             int coopOk = 0;
             cudaDeviceGetAttribute(&coopOk, cudaDevAttrCooperativeLaunch, id);
             if (coopOk) { d.frameBlocks = frameKernelMaxBlocks(false); d.frameBlocksCount = frameKernelMaxBlocks(true); }
+            d.traceBlocks = traceKernelBlocksPerSm(false) * d.smCount; d.traceBlocksCount = traceKernelBlocksPerSm(true) * d.smCount;
             cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounterSlots);
             c->devs.push_back(d);
         }
@@ -282,7 +289,8 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     if (nNodes > 0x3fffffffULL || nRefs > 0x7fffffffULL || nTri > 0x7fffffffULL / 8)
         return fail(c, XNART_ERR_UNSUPPORTED, "scene too large for 32-bit node/reference indices");
     size_t nMeshRefs = nRefs - c->sceneTree.refs.size();
-    std::vector<float4> nodes(2 * nNodes), cons(nCons), leafTri(4 * nMeshRefs), triS(5 * nTri);
+    std::vector<float4> nodes(2 * nNodes), cons(nCons), inner(8 * nCons), leafTri(4 * nMeshRefs), triS(5 * nTri);
+    bool planesShared = true;
     std::vector<int> refs(nRefs), objMeshIds(nObjMesh);
     std::vector<uint32_t> texels(nTex);
     std::vector<DevMesh> dmeshes(c->meshes.size());
@@ -298,6 +306,30 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         }
         for (size_t k = 0; k < t.consMax.size() / 3; k++)
             cons[consBase + k] = make_float4(t.consMax[3 * k], t.consMax[3 * k + 1], t.consMax[3 * k + 2], 0.0f);
+        // expansion records: the 12 planes of the 8 children + consMax + child descriptors
+        for (size_t n = 0; n < t.nodeCount(); n++) {
+            if (t.w1[n] >= 0) continue;
+            const size_t k = (size_t)(-1 - t.w1[n]), f = (size_t)t.w0[n];
+            float4* R = &inner[8 * (consBase + k)];
+            const size_t cx = f + 4, cy = f + 2, cz = f + 1;
+            R[0] = make_float4(t.lo[3 * f + 0], t.hi[3 * f + 0], t.lo[3 * cx + 0], t.hi[3 * cx + 0]);
+            R[1] = make_float4(t.lo[3 * f + 1], t.hi[3 * f + 1], t.lo[3 * cy + 1], t.hi[3 * cy + 1]);
+            R[2] = make_float4(t.lo[3 * f + 2], t.hi[3 * f + 2], t.lo[3 * cz + 2], t.hi[3 * cz + 2]);
+            R[3] = make_float4(t.consMax[3 * k], t.consMax[3 * k + 1], t.consMax[3 * k + 2], 0.0f);
+            const float pl[3][4] = {{R[0].x, R[0].y, R[0].z, R[0].w}, {R[1].x, R[1].y, R[1].z, R[1].w}, {R[2].x, R[2].y, R[2].z, R[2].w}};
+            int desc[16];
+            for (int ch = 0; ch < 8; ch++) {
+                const size_t cn = f + (size_t)ch;
+                const int h3[3] = {ch >> 2, (ch >> 1) & 1, ch & 1};
+                for (int a = 0; a < 3; a++)
+                    if (t.lo[3 * cn + a] != pl[a][2 * h3[a]] || t.hi[3 * cn + a] != pl[a][2 * h3[a] + 1]) planesShared = false;
+                if (t.w1[cn] >= 0) { desc[2 * ch] = t.w0[cn] + (int)refBase; desc[2 * ch + 1] = t.w1[cn]; }
+                else { desc[2 * ch] = (-1 - t.w1[cn]) + (int)consBase; desc[2 * ch + 1] = -1; }
+            }
+            // the node's own Min must be child 0's Min (Min + size*0): the conservative-box test relies on it
+            for (int a = 0; a < 3; a++) if (t.lo[3 * n + a] != pl[a][0]) planesShared = false;
+            std::memcpy(&R[4], desc, 64);
+        }
         std::copy(t.refs.begin(), t.refs.end(), refs.begin() + (long)refBase);
         nodeBase += t.nodeCount(); consBase += t.consMax.size() / 3; refBase += t.refs.size();
     };
@@ -307,12 +339,17 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         std::memcpy(dm.box, m.box.mn, 12);
         std::memcpy(dm.box + 3, m.box.mx, 12);
         dm.rootNode = (int)nodeBase;
+        std::memcpy(dm.rootBox, &m.tree.lo[0], 12);
+        std::memcpy(dm.rootBox + 3, &m.tree.hi[0], 12);
+        if (m.tree.w1[0] >= 0) { dm.rootA = m.tree.w0[0] + (int)refBase; dm.rootB = m.tree.w1[0]; }
+        else { dm.rootA = (-1 - m.tree.w1[0]) + (int)consBase; dm.rootB = -1; }
         dm.triBase = (int)triBase;
         dm.reflectiveness = m.reflectiveness;
         dm.oneMinusReflectiveness = 1.0f - m.reflectiveness;
         dm.refractionIndex = m.refractionIndex;
         dm.flags = m.flags;
-        dm.texOffset = (int)texBase; dm.texW = m.texW; dm.texH = m.texH; dm._pad = 0;
+        dm.texOffset = (int)texBase; dm.texW = m.texW; dm.texH = m.texH;
+        std::memset(dm._pad, 0, sizeof dm._pad);
         const size_t firstRef = refBase;
         emitTree(m.tree);
         // one intersection record per leaf reference, at the reference's own position
@@ -333,6 +370,7 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     }
     const int sceneRoot = (int)nodeBase;
     emitTree(c->sceneTree);
+    if (!planesShared) return fail(c, XNART_ERR_UNSUPPORTED, "internal: octree children do not share their split planes");
     size_t om = 0;
     for (size_t i = 0; i < c->objs.size(); i++) {
         const HostObj& o = c->objs[i];
@@ -342,12 +380,24 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         d.meshStart = (int)om; d.meshCount = (int)o.meshIds.size(); d._pad[0] = d._pad[1] = 0;
         for (int id : o.meshIds) objMeshIds[om++] = id;
     }
+    // (object, mesh) pairs in visiting order when the scene octree is one leaf (wavefront path)
+    std::vector<int2> pairs;
+    if (c->sceneTree.nodeCount() == 1 && c->sceneTree.w1[0] >= 0) {
+        for (int i = 0; i < c->sceneTree.w1[0]; i++) {
+            const int oi = c->sceneTree.refs[(size_t)c->sceneTree.w0[0] + (size_t)i];
+            for (int id : c->objs[(size_t)oi].meshIds) pairs.push_back(make_int2(oi, id));
+        }
+    }
+    c->nPairs = (int)pairs.size();
     for (DeviceState& d : c->devs) {
         CU_TRY(c, cudaSetDevice(d.dev));
         CU_TRY(c, cudaStreamSynchronize(d.stream));
         freeScene(d);
+        if (!pairs.empty()) CU_TRY(c, uploadVec(&d.pairs, pairs));
+        d.scene.pairs = d.pairs; d.scene.nPairs = (int)pairs.size();
         CU_TRY(c, uploadVec(&d.nodes, nodes));
         CU_TRY(c, uploadVec(&d.consMax, cons));
+        CU_TRY(c, uploadVec(&d.inner, inner));
         CU_TRY(c, uploadVec(&d.refs, refs));
         CU_TRY(c, uploadVec(&d.leafTri, leafTri));
         CU_TRY(c, uploadVec(&d.triS, triS));
@@ -355,7 +405,7 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         CU_TRY(c, uploadVec(&d.objs, dobjs));
         CU_TRY(c, uploadVec(&d.objMeshIds, objMeshIds));
         CU_TRY(c, uploadVec(&d.texels, texels));
-        d.scene.nodes = d.nodes; d.scene.consMax = d.consMax; d.scene.refs = d.refs;
+        d.scene.nodes = d.nodes; d.scene.consMax = d.consMax; d.scene.inner = d.inner; d.scene.refs = d.refs;
         d.scene.leafTri = d.leafTri; d.scene.triS = d.triS; d.scene.meshes = d.meshes; d.scene.objs = d.objs;
         d.scene.objMeshIds = d.objMeshIds; d.scene.texels = d.texels;
         d.scene.sceneRoot = sceneRoot; d.scene.nMeshes = (int)dmeshes.size(); d.scene.nObjs = (int)dobjs.size();
@@ -409,10 +459,12 @@ static int localRowsOf(int H, int shardIndex, int shardCount, int bandRows) {
     return rows;
 }
 
-static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned rays) {
+static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned rays, bool wave = false, int nLights = 0) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t shRays = wave ? (size_t)rays * (size_t)std::max(nLights, 1) : 0;
     size_t need = al((size_t)nodes * 16) * 2 + al((size_t)nodes * 8) + al((size_t)nodes * 4) * 2 +
                   2 * (al((size_t)rays * 16) * 2 + al((size_t)rays * 8));
+    if (wave) need += al((size_t)rays * 32) + al(shRays * 16) * 2 + al(shRays * 8) + al(shRays * 32);
     if (need > d.arenaBytes) {
         CU_TRY(c, cudaStreamSynchronize(d.stream));
         cudaFree(d.arenaBlock);
@@ -433,24 +485,36 @@ static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned ray
         A.rayD[q] = (float4*)take((size_t)rays * 16);
         A.rayIgn[q] = (int2*)take((size_t)rays * 8);
     }
+    A.hit = nullptr; A.shO = A.shD = nullptr; A.shIgn = nullptr; A.shHit = nullptr;
+    if (wave) {
+        A.hit = (int4*)take((size_t)rays * 32);
+        A.shO = (float4*)take(shRays * 16);
+        A.shD = (float4*)take(shRays * 16);
+        A.shIgn = (int2*)take(shRays * 8);
+        A.shHit = (int4*)take(shRays * 32);
+    }
     A.levelCount = d.levelWords;
     A.levelBase = d.levelWords + (kMaxLevels + 2);
     A.overflow = d.levelWords + 2 * (kMaxLevels + 2);
+    A.shadowHits = d.levelWords + 2 * (kMaxLevels + 2) + 2;
+    A.fetch = d.levelWords + 3 * (kMaxLevels + 2) + 2;
     A.counters = d.counters;
     A.nodeCapacity = nodes; A.rayCapacity = rays;
     d.arenaNodes = nodes; d.arenaRays = rays;
     return XNART_OK;
 }
 
-// Octet schedule when some MeshOctree is at least two levels deep (per-thread walks diverge there);
-// one thread per ray for leaf-sized meshes, where the walk is a short loop.
-static bool useCoop(const XnartCtx* c) {
-    if (c->traversalMode == 1) return false;
-    return c->traversalMode == 2;
-}
-// Deep octrees: the walk is latency bound, so the per-thread kernel is launched in its
-// high-occupancy build.
+// Deep octrees: the per-thread kernel is launched in its high-occupancy build.
 static bool deepScene(const XnartCtx* c) { return c->maxMeshDepth >= 2; }
+// Wavefront schedule (persistent trace kernel, wavefront.cu): the cost of a query on a deep
+// MeshOctree is heavy-tailed and a whole CastRay per thread leaves most lanes of a warp idle.
+// Needs the scene octree to be a single leaf; mode 2 forces it wherever it is available.
+static bool useWave(const XnartCtx* c, const DeviceState& d) {
+    if (c->nPairs <= 0 || d.traceBlocks <= 0 || d.traceBlocksCount <= 0) return false;
+    if (c->traversalMode == 1) return false;
+    if (c->traversalMode == 2) return true;
+    return deepScene(c);
+}
 
 static int validateFrame(XnartCtx* c, const XnartFrame* f) {
     if (!f) return fail(c, XNART_ERR_INVALID_ARGUMENT, "null frame");
@@ -485,7 +549,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     F.shardCount = f.shardCount > 1 ? f.shardCount : 1;
     F.shardBandRows = f.shardCount > 1 ? f.shardBandRows : 1;
     F.nLights = (int)c->lights.size();
-    F._pad = 0;
+    F.tiled = 0;
     const int D = f.maxReflections;
     const long long localPixels = (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
     d.lastPixels = accumulate ? d.lastPixels + localPixels : localPixels;
@@ -494,23 +558,32 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     // transparent material can fork every hit into reflection + refraction (RayTracer.cs:586-702)
     const double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
     const double raysPerPixel = c->hasTransparent ? std::ldexp(1.0, D) : 1.0;
-    const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * 80.0 + 64.0;
+    const bool wave = useWave(c, d);
+    const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * (80.0 + (wave ? 32.0 + 72.0 * std::max(F.nLights, 1) : 0.0)) + 64.0;
     long long chunk = (long long)std::floor((double)c->arenaLimit / bytesPerPixel);
     chunk = std::min<long long>(chunk, (long long)(4.0e9 / nodesPerPixel));
     chunk = std::min(chunk, localPixels);
     if (chunk < 1) return fail(c, XNART_ERR_OUT_OF_MEMORY, "arena limit too small for one pixel at this recursion depth");
     if (chunk < localPixels && chunk >= 4096) chunk -= chunk % 4096;
+    // 8x4 pixel tiles per warp when the shard is made of whole tiles (and so is every chunk)
+    {
+        const long long tileRow = 4LL * f.vpW;
+        const bool whole = (f.vpW % 8 == 0) && (localPixels % tileRow == 0);
+        if (whole && chunk < localPixels && chunk >= tileRow) chunk -= chunk % tileRow;
+        F.tiled = (whole && (chunk >= localPixels || chunk % tileRow == 0)) ? 1 : 0;
+    }
     const unsigned nodeCap = (unsigned)std::min(4.0e9, std::ceil((double)chunk * nodesPerPixel));
     const unsigned rayCap = (unsigned)std::min(4.0e9, std::ceil((double)chunk * raysPerPixel));
-    int rc = ensureArena(c, d, nodeCap, rayCap);
+    int rc = ensureArena(c, d, nodeCap, rayCap, wave, F.nLights);
     if (rc != XNART_OK) return rc;
     const int maxBlocks = d.smCount * 8;
     d.singleChunk = chunk >= localPixels;
     // Shallow scenes (every MeshOctree a leaf or one split): launch overhead of the deep, nearly
     // empty levels matters -> one cooperative launch per chunk.  Deep scenes keep one launch per
     // level in the high-occupancy build of the kernel.
-    const bool fused = c->fuseFrame && !useCoop(c) && !deepScene(c) && d.frameBlocks > 0 && d.frameBlocksCount > 0;
+    const bool fused = !wave && c->fuseFrame && !deepScene(c) && d.frameBlocks > 0 && d.frameBlocksCount > 0;
     d.lastFused = fused;
+    d.lastWave = wave;
 
     if (!accumulate) {
         CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
@@ -519,7 +592,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     for (long long p0 = 0; p0 < localPixels; p0 += chunk) {
         F.pixelBase = p0;
         F.chunkPixels = (int)std::min(chunk, localPixels - p0);
-        CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * (2 * (kMaxLevels + 2) + 2), st));
+        CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * kLevelWords, st));
         if (fused) {
             // whole chunk in one cooperative launch (levels + resolve, grid barriers in between)
             const int blocks = c->countKernels ? d.frameBlocksCount : d.frameBlocks;
@@ -529,7 +602,30 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         }
         for (int L = 0; L <= D; L++) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
-            CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, useCoop(c), deepScene(c), st));
+            if (!wave) {
+                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, deepScene(c), st));
+                c->launches++;
+                continue;
+            }
+            // wavefront: [primary rays] -> trace -> shade A (shadow rays) -> trace -> shade B (next level's rays)
+            const DevArena& A = d.arena;
+            const int tb = c->countKernels ? d.traceBlocksCount : d.traceBlocks;
+            if (L == 0) { CU_TRY(c, launchGenPrimary(F, A, maxBlocks, st)); c->launches++; }
+            const int in = L & 1;
+            TraceJob J;
+            J.rayO = A.rayO[in]; J.rayD = A.rayD[in]; J.rayIgn = A.rayIgn[in]; J.out = A.hit;
+            J.segCount = &A.levelCount[L]; J.fetch = &A.fetch[2 * L]; J.nSeg = 1; J.segStride = 0;
+            CU_TRY(c, launchTrace(d.scene, J, d.counters, tb, c->countKernels, st));
+            CU_TRY(c, launchShadeA(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, st));
+            c->launches += 2;
+            if (F.nLights > 0) {
+                TraceJob Sj;
+                Sj.rayO = A.shO; Sj.rayD = A.shD; Sj.rayIgn = A.shIgn; Sj.out = A.shHit;
+                Sj.segCount = &A.shadowHits[L]; Sj.fetch = &A.fetch[2 * L + 1]; Sj.nSeg = (unsigned)F.nLights; Sj.segStride = A.rayCapacity;
+                CU_TRY(c, launchTrace(d.scene, Sj, d.counters, tb, c->countKernels, st));
+                c->launches++;
+            }
+            CU_TRY(c, launchShadeB(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, st));
             c->launches++;
         }
         if (p0 == 0) CU_TRY(c, cudaEventRecord(d.ev[1], st));
@@ -808,16 +904,32 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
     CU_TRY(c, cudaSetDevice(d.dev));
     float *dr = nullptr, *du = nullptr, *dv = nullptr, *dd = nullptr, *dp = nullptr;
     int *di = nullptr, *dobj = nullptr, *dmesh = nullptr, *dtri = nullptr;
+    float4 *qo = nullptr, *qd = nullptr; int2* qi = nullptr; int4* qh = nullptr; unsigned* qw = nullptr;
     size_t N = (size_t)n;
-    auto cleanup = [&]() { cudaFree(dr); cudaFree(du); cudaFree(dv); cudaFree(dd); cudaFree(dp); cudaFree(di); cudaFree(dobj); cudaFree(dmesh); cudaFree(dtri); };
+    if (N > 0x7fffffffULL) return fail(c, XNART_ERR_UNSUPPORTED, "xnart_trace_rays: too many rays in one batch");
+    auto cleanup = [&]() { cudaFree(qo); cudaFree(qd); cudaFree(qi); cudaFree(qh); cudaFree(qw); cudaFree(dr); cudaFree(du); cudaFree(dv); cudaFree(dd); cudaFree(dp); cudaFree(di); cudaFree(dobj); cudaFree(dmesh); cudaFree(dtri); };
 #define TR_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(c, XNART_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(_e)); } } while (0)
     TR_TRY(cudaMalloc(&dr, N * 24)); TR_TRY(cudaMalloc(&du, N * 4)); TR_TRY(cudaMalloc(&dv, N * 4)); TR_TRY(cudaMalloc(&dd, N * 4));
     TR_TRY(cudaMalloc(&dp, N * 12)); TR_TRY(cudaMalloc(&dobj, N * 4)); TR_TRY(cudaMalloc(&dmesh, N * 4)); TR_TRY(cudaMalloc(&dtri, N * 4));
     if (ignore2) { TR_TRY(cudaMalloc(&di, N * 8)); TR_TRY(cudaMemcpyAsync(di, ignore2, N * 8, cudaMemcpyHostToDevice, d.stream)); }
     TR_TRY(cudaMemcpyAsync(dr, rays6, N * 24, cudaMemcpyHostToDevice, d.stream));
     TR_TRY(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
-    TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, useCoop(c), d.stream));
-    c->launches++;
+    if (useWave(c, d)) {
+        // same persistent kernel as the frame path: pack -> trace -> unpack
+        TR_TRY(cudaMalloc(&qo, N * 16)); TR_TRY(cudaMalloc(&qd, N * 16)); TR_TRY(cudaMalloc(&qi, N * 8)); TR_TRY(cudaMalloc(&qh, N * 32));
+        TR_TRY(cudaMalloc(&qw, 8));
+        const unsigned words[2] = {(unsigned)N, 0u};
+        TR_TRY(cudaMemcpyAsync(qw, words, 8, cudaMemcpyHostToDevice, d.stream));
+        TR_TRY(launchPackRays(dr, di, n, qo, qd, qi, d.smCount * 8, d.stream));
+        TraceJob J;
+        J.rayO = qo; J.rayD = qd; J.rayIgn = qi; J.out = qh; J.segCount = qw; J.fetch = qw + 1; J.nSeg = 1; J.segStride = 0;
+        TR_TRY(launchTrace(d.scene, J, d.counters, c->countKernels ? d.traceBlocksCount : d.traceBlocks, c->countKernels, d.stream));
+        TR_TRY(launchUnpackHits(d.scene, qh, n, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, d.stream));
+        c->launches += 3;
+    } else {
+        TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, d.stream));
+        c->launches++;
+    }
     TR_TRY(cudaMemcpyAsync(objId, dobj, N * 4, cudaMemcpyDeviceToHost, d.stream));
     TR_TRY(cudaMemcpyAsync(meshId, dmesh, N * 4, cudaMemcpyDeviceToHost, d.stream));
     TR_TRY(cudaMemcpyAsync(triId, dtri, N * 4, cudaMemcpyDeviceToHost, d.stream));
