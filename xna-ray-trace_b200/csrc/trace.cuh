@@ -42,6 +42,18 @@ struct RayPre {
     int oct;    // bit 2/1/0 set: d.x / d.y / d.z negative -> children visited as (i ^ oct)
 };
 
+// 256-bit read-only load (LDG.E.256 on sm_100a): a divergent access costs the L1 one wavefront per
+// lane and per INSTRUCTION, so the 128-byte node record and the 64-byte triangle record are fetched
+// with 32-byte loads (ncu: l1tex__data_pipe_lsu_wavefronts was the binding unit with 16-byte loads).
+struct __align__(32) F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const void* p) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ bool finite3(V3 v) {
     return (fabsf(v.x) <= FLT_MAX) && (fabsf(v.y) <= FLT_MAX) && (fabsf(v.z) <= FLT_MAX);
 }
@@ -82,6 +94,29 @@ __device__ __forceinline__ bool slab(float3 mn, float3 mx, const RayPre& r, floa
     return ok && !(tmin > tmax);
 }
 
+// Vector3.Transform with the matrix fetched as four 16-byte rows (SceneObject.World / InverseWorld
+// live in global memory: 4 loads instead of 12).
+struct M43 { float4 r0, r1, r2, r3; };
+__device__ __forceinline__ M43 loadM43(const float* __restrict__ m) {
+    const float4* __restrict__ q = reinterpret_cast<const float4*>(m);
+    M43 r;
+    r.r0 = __ldg(&q[0]); r.r1 = __ldg(&q[1]); r.r2 = __ldg(&q[2]); r.r3 = __ldg(&q[3]);
+    return r;
+}
+__device__ __forceinline__ V3 transform43(V3 p, const M43& m) {
+    return mk((((p.x * m.r0.x) + (p.y * m.r1.x)) + (p.z * m.r2.x)) + m.r3.x,
+              (((p.x * m.r0.y) + (p.y * m.r1.y)) + (p.z * m.r2.y)) + m.r3.y,
+              (((p.x * m.r0.z) + (p.y * m.r1.z)) + (p.z * m.r2.z)) + m.r3.z);
+}
+
+// Mesh.RayIntersects (Mesh.cs:34-39): slab test on Mesh.MeshBoundingBox (bytes 0..23 of DevMesh).
+__device__ __forceinline__ bool meshBoxSlab(const DevMesh* __restrict__ M, const RayPre& r) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(M->box));
+    const float2 b1 = __ldg(reinterpret_cast<const float2*>(M->box + 4));
+    float tb;
+    return slab(make_float3(b0.x, b0.y, b0.z), make_float3(b0.w, b1.x, b1.y), r, tb);
+}
+
 struct MeshHit {
     int tri;       // mesh-relative triangle index, -1 = none
     int key;       // position of the winning leaf reference in refs[] / leafTri[]
@@ -91,7 +126,8 @@ struct MeshHit {
 struct StackEntry { int node; float t; };
 
 // Mesh-walk stack entry: a child descriptor (see device_types.h, inner[8k+4..7]) and its entry distance.
-struct WalkEntry { int a, b; float t; };
+// 16 bytes so that a push is ONE local store and a pop ONE local load (STL.128 / LDL.128).
+typedef int4 WalkEntry;  // (a, b, bits(t), 0)
 
 #ifndef XN_LEAF_CHUNK
 #define XN_LEAF_CHUNK 12   // triangles tested per visit of the leaf phase (longer leaves are resumed)
@@ -103,9 +139,8 @@ struct WalkEntry { int a, b; float t; };
 // State of one MeshOctree.GetRayIntersection walk (all scalars: lives in registers).
 struct Walk {
     float K;            // entry distance of the nearest leaf that produced an accepted triangle
-    bool found;
     float bd, bu, bv;   // best candidate of the current K group
-    int btri, bkey;
+    int btri, bkey;     // btri < 0: nothing accepted yet
     int ca, cb;         // held node: leaf (first ref, remaining count) or inner (record, -1)
     float ct;           // its entry distance
     bool have;
@@ -118,23 +153,26 @@ struct Walk {
 // are void); at tcur == K the candidates merge by (distance, position) — positions increase inside
 // a leaf, so this equals "strict < keeps the first of equal distances" followed by the group merge.
 template <bool COUNT>
-__device__ __forceinline__ void testTriangle(const float4 n4, const float4 a, const float4 b, const float4 c, int pos, const RayPre& r,
+__device__ __forceinline__ void testTriangle(const F8 A, const float4* __restrict__ T4, int pos, const RayPre& r,
                                              int ignoreTri, Walk& w, Ctr& ctr) {
-    const int ti = __float_as_int(n4.w);
+    // A = (surfaceNormal, triangle index | v1, -): enough to reject the ignored triangle and back faces;
+    // the edge vectors (second 32 bytes of the record) are fetched only for the full test
+    const int ti = __float_as_int(A.a.w);
     if (COUNT) ctr.nTriRef++;
     if (ti == ignoreTri) return;  // ignoreTriangle != triangles[i] (reference identity)
     // dot(surfaceNormal, D) > 0 -> back face (RayExtensions.cs:48-51)
-    if (dot(mk(n4.x, n4.y, n4.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; return; }
+    if (dot(mk(A.a.x, A.a.y, A.a.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; return; }
     if (COUNT) ctr.nTriFull++;
-    V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z);
-    V3 T = sub(r.o, mk(a.x, a.y, a.z));
+    const F8 B = ldg256(T4 + 2);
+    V3 E1 = mk(B.a.x, B.a.y, B.a.z), E2 = mk(B.b.x, B.b.y, B.b.z);
+    V3 T = sub(r.o, mk(A.b.x, A.b.y, A.b.z));
     V3 P = cross(r.d, E2);
     V3 Q = cross(T, E1);
     float row1 = dot(Q, E2), row2 = dot(P, T), row3 = dot(Q, r.d);
     float inv = 1.0f / dot(P, E1);
     float dist = inv * row1, uu = inv * row2, vv = inv * row3;
     if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f) {
-        if (!w.found || w.ct < w.K) { w.found = true; w.K = w.ct; w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
+        if (w.btri < 0 || w.ct < w.K) { w.K = w.ct; w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
         else if (dist < w.bd || (dist == w.bd && pos < w.bkey)) { w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
     }
 }
@@ -156,26 +194,30 @@ template <bool COUNT>
 __device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const RayPre& r, Walk& w, Ctr& ctr) {
     float t0;
     if (COUNT) ctr.nBox++;
-    if (!slab(make_float3(M->rootBox[0], M->rootBox[1], M->rootBox[2]), make_float3(M->rootBox[3], M->rootBox[4], M->rootBox[5]), r, t0))
-        return false;
-    w.K = INFINITY; w.found = false; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
-    w.ca = M->rootA; w.cb = M->rootB; w.ct = t0; w.have = true; w.sp = 0;
+    // rootBox[0..5], rootA, rootB = bytes 24..55 of DevMesh
+    const float2 rb0 = __ldg(reinterpret_cast<const float2*>(M->rootBox));
+    const float4 rb1 = __ldg(reinterpret_cast<const float4*>(M->rootBox + 2));
+    if (!slab(make_float3(rb0.x, rb0.y, rb1.x), make_float3(rb1.y, rb1.z, rb1.w), r, t0)) return false;
+    const int2 rd = __ldg(reinterpret_cast<const int2*>(&M->rootA));
+    w.K = INFINITY; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
+    w.ca = rd.x; w.cb = rd.y; w.ct = t0; w.have = true; w.sp = 0;
     return true;
 }
 
 // Returns true when the walk is over (nothing held, stack empty).
-template <bool COUNT>
+template <bool COUNT, int STEPS = XN_DESCEND_MAX>
 __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, Walk& w, WalkEntry* __restrict__ stack, Ctr& ctr) {
     const bool ox = (r.oct & 4) != 0, oy = (r.oct & 2) != 0, oz = (r.oct & 1) != 0;
 #pragma unroll 1
-    for (int step = 0; step < XN_DESCEND_MAX; step++) {
+    for (int step = 0; step < STEPS; step++) {
         if (!w.have) {
             // pop the next entry that survives the cheap prune test
             while (w.sp > 0) {
                 w.sp--;
                 const WalkEntry e = stack[w.sp];
-                if (e.b >= 0 && e.t > w.K) continue;  // leaf entered after K
-                w.ca = e.a; w.cb = e.b; w.ct = e.t; w.have = true;
+                const float et = __int_as_float(e.z);
+                if (e.y >= 0 && et > w.K) continue;  // leaf entered after K
+                w.ca = e.x; w.cb = e.y; w.ct = et; w.have = true;
                 break;
             }
             if (!w.have) return true;
@@ -183,15 +225,27 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
         if (w.cb >= 0) return false;  // a leaf
         // ---- internal node: slab-test all 8 children (MeshOctree.cs:336-339)
         const float4* __restrict__ R = S.inner + 8 * (size_t)w.ca;
-        const float4 qx = __ldg(&R[0]), qy = __ldg(&R[1]), qz = __ldg(&R[2]);
-        const int2* __restrict__ D2 = reinterpret_cast<const int2*>(R + 4);
-        // descriptors in front-to-back position order: position p holds child p ^ octant
+        // the 128-byte record in four 32-byte loads: planes x,y | planes z, consMax | descriptors
+        const F8 Rxy = ldg256(R), Rzc = ldg256(R + 2);
+        const float4 qx = Rxy.a, qy = Rxy.b, qz = Rzc.a;
+        // descriptors in front-to-back position order: position p holds child p ^ octant.  The x bit
+        // of the octant picks which half of the 64 descriptor bytes is loaded first, the y and z bits
+        // are applied as register swaps.
+        const F8 Dn = ldg256(R + (ox ? 6 : 4)), Df = ldg256(R + (ox ? 4 : 6));
         int2 ds[8];
-#pragma unroll
-        for (int p = 0; p < 8; p++) ds[p] = __ldg(&D2[p ^ r.oct]);
+        {
+            const int2 e0 = make_int2(__float_as_int(Dn.a.x), __float_as_int(Dn.a.y)), e1 = make_int2(__float_as_int(Dn.a.z), __float_as_int(Dn.a.w));
+            const int2 e2 = make_int2(__float_as_int(Dn.b.x), __float_as_int(Dn.b.y)), e3 = make_int2(__float_as_int(Dn.b.z), __float_as_int(Dn.b.w));
+            const int2 f0 = make_int2(__float_as_int(Df.a.x), __float_as_int(Df.a.y)), f1 = make_int2(__float_as_int(Df.a.z), __float_as_int(Df.a.w));
+            const int2 f2 = make_int2(__float_as_int(Df.b.x), __float_as_int(Df.b.y)), f3 = make_int2(__float_as_int(Df.b.z), __float_as_int(Df.b.w));
+            const int2 g0 = oy ? e2 : e0, g1 = oy ? e3 : e1, g2 = oy ? e0 : e2, g3 = oy ? e1 : e3;
+            const int2 h0 = oy ? f2 : f0, h1 = oy ? f3 : f1, h2 = oy ? f0 : f2, h3 = oy ? f1 : f3;
+            ds[0] = oz ? g1 : g0; ds[1] = oz ? g0 : g1; ds[2] = oz ? g3 : g2; ds[3] = oz ? g2 : g3;
+            ds[4] = oz ? h1 : h0; ds[5] = oz ? h0 : h1; ds[6] = oz ? h3 : h2; ds[7] = oz ? h2 : h3;
+        }
         if (w.ct > w.K) {
             // entered after K: prune on the conservative box (own Min, consMax)
-            const float4 qc = __ldg(&R[3]);
+            const float4 qc = Rzc.b;
             float tcns;
             bool h = slab(make_float3(qx.x, qy.x, qz.x), make_float3(qc.x, qc.y, qc.z), r, tcns);
             if (h && tcns > w.K) { w.have = false; continue; }
@@ -220,7 +274,7 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
                 // empty leaves are dropped; a leaf entered after K can never matter; internal nodes are
                 // re-examined when popped (conservative box)
                 if (!(tmin > tmax) && d.y != 0 && (d.y < 0 || !(tmin > w.K))) {
-                    if (w.have) { stack[w.sp].a = w.ca; stack[w.sp].b = w.cb; stack[w.sp].t = w.ct; w.sp++; }
+                    if (w.have) { stack[w.sp] = make_int4(w.ca, w.cb, __float_as_int(w.ct), 0); w.sp++; }
                     w.ca = d.x; w.cb = d.y; w.ct = tmin; w.have = true;
                 }
             }
@@ -237,7 +291,7 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
                                     make_float3(i ? hx[1] : hx[0], j ? hy[1] : hy[0], k ? hz[1] : hz[0]), r, tc);
                 const int2 d = ds[p];
                 if (h && d.y != 0 && (d.y < 0 || !(tc > w.K))) {
-                    if (w.have) { stack[w.sp].a = w.ca; stack[w.sp].b = w.cb; stack[w.sp].t = w.ct; w.sp++; }
+                    if (w.have) { stack[w.sp] = make_int4(w.ca, w.cb, __float_as_int(w.ct), 0); w.sp++; }
                     w.ca = d.x; w.cb = d.y; w.ct = tc; w.have = true;
                 }
             }
@@ -252,11 +306,13 @@ __device__ __forceinline__ void walkLeaf(const DevScene& S, const RayPre& r, int
     if (!(w.have && w.cb >= 0)) return;
     const int n = min(w.cb, XN_LEAF_CHUNK);
     const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)w.ca;
+    if (n <= 0) { if (w.cb == 0) w.have = false; return; }
+    F8 A = ldg256(T4);
 #pragma unroll 1
     for (int i = 0; i < n; i++, T4 += 4) {
-        // all four loads of the record are issued together (one round trip)
-        const float4 n4 = __ldg(&T4[0]), a = __ldg(&T4[1]), b = __ldg(&T4[2]), c = __ldg(&T4[3]);
-        testTriangle<COUNT>(n4, a, b, c, w.ca + i, r, ignoreTri, w, ctr);
+        const F8 cur = A;
+        if (i + 1 < n) A = ldg256(T4 + 4);  // next record's first half is in flight during this test
+        testTriangle<COUNT>(cur, T4, w.ca + i, r, ignoreTri, w, ctr);
     }
     w.ca += n; w.cb -= n;
     if (w.cb == 0) w.have = false;
@@ -274,7 +330,7 @@ __device__ __forceinline__ bool traceMesh(const DevScene& S, const DevMesh* __re
         walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
     }
     out.tri = w.btri; out.key = w.bkey; out.u = w.bu; out.v = w.bv; out.d = w.bd;
-    return w.found;
+    return w.btri >= 0;
 }
 
 struct Hit {
@@ -291,8 +347,9 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
     const DevObj* __restrict__ O = &S.objs[objIdx];
     // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (:358-364)
     V3 rdp = add(ro, rd);
-    V3 v1 = transform43(ro, O->inv);
-    V3 v2 = transform43(rdp, O->inv);
+    const M43 Wi = loadM43(O->inv);
+    V3 v1 = transform43(ro, Wi);
+    V3 v2 = transform43(rdp, Wi);
     V3 dd = normalize(sub(v2, v1));
     if (!finite3(v1) || !finite3(dd)) return;  // a non-finite ray fails every triangle test (NaN comparisons)
     RayPre r = prepRay(v1, dd);
@@ -300,10 +357,8 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
     for (int mi = 0; mi < mc; mi++) {
         int meshId = __ldg(&S.objMeshIds[ms + mi]);
         const DevMesh* __restrict__ M = &S.meshes[meshId];
-        float tb;
         if (COUNT) ctr.nBox++;
-        // Mesh.RayIntersects (Mesh.cs:34-39)
-        if (!slab(make_float3(M->box[0], M->box[1], M->box[2]), make_float3(M->box[3], M->box[4], M->box[5]), r, tb)) continue;
+        if (!meshBoxSlab(M, r)) continue;
         MeshHit mh;
         int ign = (ignMesh == meshId) ? ignTri : -1;
         const bool ok = traceMesh<COUNT>(S, M, r, ign, mh, ctr);

@@ -30,6 +30,12 @@
 #ifndef XN_TRACE_MIN_BLOCKS
 #define XN_TRACE_MIN_BLOCKS 4
 #endif
+#ifndef XN_TRACE_DESCEND
+#define XN_TRACE_DESCEND 2  // node expansions per DESCEND round of the persistent kernel
+#endif
+#ifndef XN_REFILL_MIN
+#define XN_REFILL_MIN 16    // idle lanes that trigger a refill while other lanes are still walking
+#endif
 
 namespace xn {
 
@@ -60,28 +66,29 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
     Ctr ctr;
     ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
 
+    // Per-lane state kept small on purpose (64 registers, 4 blocks per SM): the world-space ray is
+    // re-read from the batch when a lane moves on to another (object, mesh) pair, and the best hit so
+    // far lives in the output record (written when a pair improves it), only its distance in a register.
     int slot = -1;            // ray slot this lane owns, -1 = idle
     int pi = 0;               // (object, mesh) pair being tried / walked
     bool walking = false;
     bool exhausted = false;   // warp-uniform: the batch has no more rays to hand out
-    V3 wo = mk(0.0f, 0.0f, 0.0f), wd = wo;  // world-space ray
-    int ignM = -1, ignT = -1;
     RayPre r;                 // object-space ray of the pair being walked
-    r.o = r.d = r.inv = wo; r.par = r.oct = 0;
+    r.o = r.d = r.inv = mk(0.0f, 0.0f, 0.0f); r.par = r.oct = 0;
     int ignoreTri = -1;
     Walk w;
-    w.K = INFINITY; w.found = false; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
+    w.K = INFINITY; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
     w.ca = w.cb = 0; w.ct = 0.0f; w.have = false; w.sp = 0;
-    // best hit over the pairs tried so far (OctreeSpatialManager.cs:371-377: strict <, first wins)
-    float bestD = FLT_MAX, bestU = 0.0f, bestV = 0.0f;
-    int bestPair = -1, bestTri = -1, bestKey = 0;
+    float bestD = FLT_MAX;    // minDistance over the pairs tried so far (OctreeSpatialManager.cs:371-377)
 
     const float4 slo = __ldg(&S.nodes[2 * S.sceneRoot]), shi = __ldg(&S.nodes[2 * S.sceneRoot + 1]);
 
     for (;;) {
         // ---- FETCH: idle lanes take the next rays of the batch
+        // (ray set-up runs with only the refilled lanes active, so refills are batched: at least
+        // XN_REFILL_MIN idle lanes, or nothing else to do)
         const unsigned idleMask = __ballot_sync(FULL, slot < 0);
-        if (idleMask != 0u && !exhausted) {
+        if (!exhausted && (__popc(idleMask) >= XN_REFILL_MIN || __all_sync(FULL, !walking))) {
             const unsigned n = (unsigned)__popc(idleMask);
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(J.fetch, n);
@@ -92,14 +99,12 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
                     unsigned q = 0, h = i;
                     if (J.nSeg > 1) { q = i / segCount; h = i - q * segCount; }
                     slot = (int)(q * J.segStride + h);
-                    const float4 o4 = J.rayO[slot], d4 = J.rayD[slot];
-                    const int2 ig = J.rayIgn[slot];
-                    wo = mk(o4.x, o4.y, o4.z); wd = mk(d4.x, d4.y, d4.z);
-                    ignM = ig.x; ignT = ig.y;
                     pi = 0; walking = false;
-                    bestD = FLT_MAX; bestPair = -1;
+                    bestD = FLT_MAX;
                     // a non-finite ray fails every triangle test; the scene root must be hit
                     // (OctreeSpatialManager.cs:457-461)
+                    const float4 o4 = J.rayO[slot], d4 = J.rayD[slot];
+                    const V3 wo = mk(o4.x, o4.y, o4.z), wd = mk(d4.x, d4.y, d4.z);
                     bool ok = finite3(wo) && finite3(wd);
                     if (ok) {
                         const RayPre rw = prepRay(wo, wd);
@@ -116,49 +121,61 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
 
         // ---- SETUP: lanes between walks pick their next (object, mesh) pair, or finish the ray
         if (slot >= 0 && !walking) {
-            while (pi < S.nPairs) {
-                const int2 pr = __ldg(&S.pairs[pi]);
-                const DevObj* __restrict__ O = &S.objs[pr.x];
-                // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (OctreeSpatialManager.cs:358-364)
-                const V3 v1 = transform43(wo, O->inv);
-                const V3 v2 = transform43(add(wo, wd), O->inv);
-                const V3 dd = normalize(sub(v2, v1));
-                if (!finite3(v1) || !finite3(dd)) { pi++; continue; }
-                r = prepRay(v1, dd);
-                const DevMesh* __restrict__ M = &S.meshes[pr.y];
-                float tb;
-                if (COUNT) ctr.nBox++;
-                // Mesh.RayIntersects (Mesh.cs:34-39)
-                if (!slab(make_float3(M->box[0], M->box[1], M->box[2]), make_float3(M->box[3], M->box[4], M->box[5]), r, tb)) { pi++; continue; }
-                ignoreTri = (ignM == pr.y) ? ignT : -1;
-                if (!walkStart<COUNT>(M, r, w, ctr)) { pi++; continue; }
-                walking = true;
-                break;
+            if (pi < S.nPairs) {
+                const float4 o4 = J.rayO[slot], d4 = J.rayD[slot];
+                const int2 ig = J.rayIgn[slot];
+                const V3 wo = mk(o4.x, o4.y, o4.z), wd = mk(d4.x, d4.y, d4.z);
+                do {
+                    const int2 pr = __ldg(&S.pairs[pi]);
+                    const DevObj* __restrict__ O = &S.objs[pr.x];
+                    // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (OctreeSpatialManager.cs:358-364)
+                    const M43 Wi = loadM43(O->inv);
+                    const V3 v1 = transform43(wo, Wi);
+                    const V3 v2 = transform43(add(wo, wd), Wi);
+                    const V3 dd = normalize(sub(v2, v1));
+                    if (!finite3(v1) || !finite3(dd)) { pi++; continue; }
+                    r = prepRay(v1, dd);
+                    const DevMesh* __restrict__ M = &S.meshes[pr.y];
+                    if (COUNT) ctr.nBox++;
+                    if (!meshBoxSlab(M, r)) { pi++; continue; }
+                    ignoreTri = (ig.x == pr.y) ? ig.y : -1;
+                    if (!walkStart<COUNT>(M, r, w, ctr)) { pi++; continue; }
+                    walking = true;
+                } while (!walking && pi < S.nPairs);
             }
             if (!walking) {
-                // every pair tried: the ray is finished
-                int4 a = make_int4(-1, -1, -1, 0), b = make_int4(0, 0, 0, 0);
-                if (bestPair >= 0) {
-                    const int2 pr = __ldg(&S.pairs[bestPair]);
-                    a = make_int4(pr.x, pr.y, bestTri, bestKey);
-                    b = make_int4(__float_as_int(bestU), __float_as_int(bestV), __float_as_int(bestD), 1);
+                // every pair tried: the ray is finished (a hit was written when it became the best)
+                if (bestD == FLT_MAX) {
+                    J.out[2 * (size_t)slot] = make_int4(-1, -1, -1, 0);
+                    J.out[2 * (size_t)slot + 1] = make_int4(0, 0, 0, 0);
                 }
-                J.out[2 * (size_t)slot] = a;
-                J.out[2 * (size_t)slot + 1] = b;
                 slot = -1;
             }
         }
         __syncwarp();
 
-        // ---- DESCEND, then LEAF
+        // ---- one phase per round, chosen by majority: LEAF (lanes holding a leaf test a chunk of its
+        // triangles) or DESCEND (the others pop / expand one node).  Lanes of the minority wait, so each
+        // phase runs with most of the walking lanes active instead of a few.
+        const bool wantLeaf = walking && w.have && w.cb >= 0;
+        const unsigned nLeaf = (unsigned)__popc(__ballot_sync(FULL, wantLeaf));
+        const unsigned nDesc = (unsigned)__popc(__ballot_sync(FULL, walking && !wantLeaf));
         bool over = false;
-        if (walking) over = walkDescend<COUNT>(S, r, w, stack, ctr);
-        __syncwarp();
-        if (walking && !over) walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+        if (nLeaf >= nDesc) {
+            if (wantLeaf) walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+        } else {
+            if (walking && !wantLeaf) over = walkDescend<COUNT, XN_TRACE_DESCEND>(S, r, w, stack, ctr);
+        }
         __syncwarp();
         if (walking && over) {
-            // minDistance bookkeeping of the object loop (OctreeSpatialManager.cs:370-377)
-            if (w.found && w.bd < bestD) { bestD = w.bd; bestU = w.bu; bestV = w.bv; bestTri = w.btri; bestKey = w.bkey; bestPair = pi; }
+            // minDistance bookkeeping of the object loop (OctreeSpatialManager.cs:370-377): strict <,
+            // so the first of equal distances stays
+            if (w.btri >= 0 && w.bd < bestD) {
+                bestD = w.bd;
+                const int2 pr = __ldg(&S.pairs[pi]);
+                J.out[2 * (size_t)slot] = make_int4(pr.x, pr.y, w.btri, w.bkey);
+                J.out[2 * (size_t)slot + 1] = make_int4(__float_as_int(w.bu), __float_as_int(w.bv), __float_as_int(w.bd), 1);
+            }
             pi++;
             walking = false;
         }
