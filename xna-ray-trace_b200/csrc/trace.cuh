@@ -130,7 +130,7 @@ struct StackEntry { int node; float t; };
 typedef int4 WalkEntry;  // (a, b, bits(t), 0)
 
 #ifndef XN_LEAF_CHUNK
-#define XN_LEAF_CHUNK 12   // triangles tested per visit of the leaf phase (longer leaves are resumed)
+#define XN_LEAF_CHUNK 16   // triangles tested per visit of the leaf phase (<= 32; longer leaves are resumed)
 #endif
 #ifndef XN_DESCEND_MAX
 #define XN_DESCEND_MAX 4   // node expansions per visit of the descend phase
@@ -147,33 +147,25 @@ struct Walk {
     int sp;
 };
 
-// One triangle of a leaf: IntersectsTriangleBackfaceCulling (RayExtensions.cs:42-75) and the
-// closest-hit bookkeeping of MeshOctree.GetRayIntersection (MeshOctree.cs:286-304) restated per
-// triangle: an accepted triangle of a leaf entered at tcur < K opens a new group (older candidates
-// are void); at tcur == K the candidates merge by (distance, position) — positions increase inside
-// a leaf, so this equals "strict < keeps the first of equal distances" followed by the group merge.
-template <bool COUNT>
-__device__ __forceinline__ void testTriangle(const F8 A, const float4* __restrict__ T4, int pos, const RayPre& r,
-                                             int ignoreTri, Walk& w, Ctr& ctr) {
-    // A = (surfaceNormal, triangle index | v1, -): enough to reject the ignored triangle and back faces;
-    // the edge vectors (second 32 bytes of the record) are fetched only for the full test
-    const int ti = __float_as_int(A.a.w);
-    if (COUNT) ctr.nTriRef++;
-    if (ti == ignoreTri) return;  // ignoreTriangle != triangles[i] (reference identity)
-    // dot(surfaceNormal, D) > 0 -> back face (RayExtensions.cs:48-51)
-    if (dot(mk(A.a.x, A.a.y, A.a.z), r.d) > 0.0f) { if (COUNT) ctr.nTriCulled++; return; }
-    if (COUNT) ctr.nTriFull++;
-    const F8 B = ldg256(T4 + 2);
+// The full part of IntersectsTriangleBackfaceCulling (RayExtensions.cs:52-75) for a triangle that
+// passed the back-face test, and the closest-hit bookkeeping of MeshOctree.GetRayIntersection
+// (MeshOctree.cs:286-304) restated per triangle.  The reference keeps, per group of leaves with a
+// bit-equal entry distance, the accepted triangle of minimum distance, `distance < minDistance`
+// with minDistance starting at float.MaxValue (:294), first of equal distances.  Here: an accepted
+// triangle of a leaf entered at ct < K opens a new group (older candidates are void: reset to the
+// MaxValue sentinel); inside a group candidates merge by (distance, position in refs[]) — positions
+// increase in the reference's visiting order.
+__device__ __forceinline__ void fullTriangleTest(const float4 nt, const float4 v1, const F8 B, int pos, const RayPre& r, Walk& w) {
     V3 E1 = mk(B.a.x, B.a.y, B.a.z), E2 = mk(B.b.x, B.b.y, B.b.z);
-    V3 T = sub(r.o, mk(A.b.x, A.b.y, A.b.z));
+    V3 T = sub(r.o, mk(v1.x, v1.y, v1.z));
     V3 P = cross(r.d, E2);
     V3 Q = cross(T, E1);
     float row1 = dot(Q, E2), row2 = dot(P, T), row3 = dot(Q, r.d);
     float inv = 1.0f / dot(P, E1);
     float dist = inv * row1, uu = inv * row2, vv = inv * row3;
-    if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f) {
-        if (w.btri < 0 || w.ct < w.K) { w.K = w.ct; w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
-        else if (dist < w.bd || (dist == w.bd && pos < w.bkey)) { w.bd = dist; w.bu = uu; w.bv = vv; w.btri = ti; w.bkey = pos; }
+    if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f && dist < FLT_MAX) {
+        if (w.btri < 0 || w.ct < w.K) { w.K = w.ct; w.bd = FLT_MAX; w.bkey = INT_MAX; }
+        if (dist < w.bd || (dist == w.bd && pos < w.bkey)) { w.bd = dist; w.bu = uu; w.bv = vv; w.btri = __float_as_int(nt.w); w.bkey = pos; }
     }
 }
 
@@ -300,22 +292,87 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
     return false;
 }
 
-// Up to XN_LEAF_CHUNK triangles of the held leaf's containingObjects (MeshOctree.cs:286-304).
+// Up to XN_LEAF_CHUNK (<= 32) triangles of the held leaf's containingObjects (MeshOctree.cs:286-304),
+// in two passes so that the lanes of a warp do not all pay for the longest path of every triangle:
+//   pass 1  the reference-identity and back-face tests (RayExtensions.cs:46-51) on the first 16 bytes
+//           of each record (surfaceNormal, triangle index) -> bit mask of the triangles to test fully
+//   pass 2  the full test for the survivors, in list order.
 template <bool COUNT>
 __device__ __forceinline__ void walkLeaf(const DevScene& S, const RayPre& r, int ignoreTri, Walk& w, Ctr& ctr) {
     if (!(w.have && w.cb >= 0)) return;
     const int n = min(w.cb, XN_LEAF_CHUNK);
     const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)w.ca;
-    if (n <= 0) { if (w.cb == 0) w.have = false; return; }
-    F8 A = ldg256(T4);
-#pragma unroll 1
-    for (int i = 0; i < n; i++, T4 += 4) {
-        const F8 cur = A;
-        if (i + 1 < n) A = ldg256(T4 + 4);  // next record's first half is in flight during this test
-        testTriangle<COUNT>(cur, T4, w.ca + i, r, ignoreTri, w, ctr);
+    unsigned m = 0u;
+#pragma unroll 4
+    for (int i = 0; i < n; i++) {
+        const float4 nt = __ldg(&T4[4 * i]);
+        const bool ign = __float_as_int(nt.w) == ignoreTri;          // ignoreTriangle != triangles[i] (reference identity)
+        const bool back = dot(mk(nt.x, nt.y, nt.z), r.d) > 0.0f;     // dot(surfaceNormal, D) > 0 -> back face
+        if (COUNT) { ctr.nTriRef++; if (!ign) { if (back) ctr.nTriCulled++; else ctr.nTriFull++; } }
+        if (!ign && !back) m |= 1u << i;
+    }
+    while (m) {
+        const int i = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const float4* __restrict__ R = T4 + 4 * i;
+        const F8 A = ldg256(R), B = ldg256(R + 2);
+        fullTriangleTest(A.a, A.b, B, w.ca + i, r, w);
     }
     w.ca += n; w.cb -= n;
     if (w.cb == 0) w.have = false;
+}
+
+// The whole warp on ONE lane's leaf: lane j tests triangles j, j+32, ... of the leaf held by lane
+// `src`, the candidates are reduced by (distance, position) and the owner applies them to its
+// walk.  Used when only a few lanes of a warp hold leaves (the tail of a batch, where a handful of
+// grazing rays walk hundreds of leaves one after the other): a 50-triangle leaf costs two steps
+// instead of fifty.  The minimum over a set does not depend on the order of its elements, so the
+// owner ends in exactly the state the sequential loop would have produced.  Must be called by all
+// 32 lanes; `r`, `ignoreTri`, `w` are the caller's own (only lane src's are used / updated).
+template <bool COUNT>
+__device__ __forceinline__ void walkLeafWarp(const DevScene& S, int src, const RayPre& r, int ignoreTri, Walk& w, Ctr& ctr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u);
+    RayPre q;
+    q.o = mk(__shfl_sync(FULL, r.o.x, src), __shfl_sync(FULL, r.o.y, src), __shfl_sync(FULL, r.o.z, src));
+    q.d = mk(__shfl_sync(FULL, r.d.x, src), __shfl_sync(FULL, r.d.y, src), __shfl_sync(FULL, r.d.z, src));
+    q.inv = q.o; q.par = 0; q.oct = 0;  // unused by the triangle test
+    const int ign = __shfl_sync(FULL, ignoreTri, src);
+    const int first = __shfl_sync(FULL, w.ca, src), n = __shfl_sync(FULL, w.cb, src);
+    Walk c;  // this lane's candidate: reuse the bookkeeping with an "open group" that accepts anything
+    c.K = 0.0f; c.ct = 0.0f; c.bd = FLT_MAX; c.bu = c.bv = 0.0f; c.btri = -1; c.bkey = INT_MAX;
+    c.ca = c.cb = 0; c.have = false; c.sp = 0;
+    const float4* __restrict__ T4 = S.leafTri + 4 * (size_t)first;
+    for (int i = lane; i < n; i += 32) {
+        const float4* __restrict__ R = T4 + 4 * i;
+        const F8 A = ldg256(R);
+        const bool ig = __float_as_int(A.a.w) == ign;
+        const bool back = dot(mk(A.a.x, A.a.y, A.a.z), q.d) > 0.0f;
+        if (COUNT) { ctr.nTriRef++; if (!ig) { if (back) ctr.nTriCulled++; else ctr.nTriFull++; } }
+        if (!ig && !back) {
+            const F8 B = ldg256(R + 2);
+            // c.btri >= 0 after the first accepted triangle and c.ct == c.K: plain (distance, position) merge
+            fullTriangleTest(A.a, A.b, B, first + i, q, c);
+        }
+    }
+    // minimum (distance, position) over the lanes
+    float d = c.bd;
+    int key = c.bkey, from = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float d2 = __shfl_xor_sync(FULL, d, o);
+        const int k2 = __shfl_xor_sync(FULL, key, o), f2 = __shfl_xor_sync(FULL, from, o);
+        if (d2 < d || (d2 == d && k2 < key)) { d = d2; key = k2; from = f2; }
+    }
+    const float bu = __shfl_sync(FULL, c.bu, from), bv = __shfl_sync(FULL, c.bv, from);
+    const int bt = __shfl_sync(FULL, c.btri, from);
+    if (lane == src) {
+        if (bt >= 0) {
+            if (w.btri < 0 || w.ct < w.K) { w.K = w.ct; w.bd = FLT_MAX; w.bkey = INT_MAX; }
+            if (d < w.bd || (d == w.bd && key < w.bkey)) { w.bd = d; w.bu = bu; w.bv = bv; w.btri = bt; w.bkey = key; }
+        }
+        w.ca += n; w.cb = 0; w.have = false;
+    }
 }
 
 // One thread, one ray: the whole walk.

@@ -33,8 +33,11 @@
 #ifndef XN_TRACE_DESCEND
 #define XN_TRACE_DESCEND 2  // node expansions per DESCEND round of the persistent kernel
 #endif
+#ifndef XN_COOP_LEAF_MAX
+#define XN_COOP_LEAF_MAX 12 // with at most this many lanes holding leaves, the warp tests each leaf cooperatively
+#endif
 #ifndef XN_REFILL_MIN
-#define XN_REFILL_MIN 16    // idle lanes that trigger a refill while other lanes are still walking
+#define XN_REFILL_MIN 24    // idle lanes that trigger a refill while other lanes are still walking
 #endif
 
 namespace xn {
@@ -162,7 +165,17 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
         const unsigned nDesc = (unsigned)__popc(__ballot_sync(FULL, walking && !wantLeaf));
         bool over = false;
         if (nLeaf >= nDesc) {
-            if (wantLeaf) walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+            if (nLeaf <= XN_COOP_LEAF_MAX) {
+                // few lanes hold leaves: the whole warp serves them one after the other
+                unsigned lm = __ballot_sync(FULL, wantLeaf);
+                while (lm) {
+                    const int src = __ffs((int)lm) - 1;
+                    lm &= lm - 1u;
+                    walkLeafWarp<COUNT>(S, src, r, ignoreTri, w, ctr);
+                }
+            } else if (wantLeaf) {
+                walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+            }
         } else {
             if (walking && !wantLeaf) over = walkDescend<COUNT, XN_TRACE_DESCEND>(S, r, w, stack, ctr);
         }
