@@ -10,7 +10,8 @@ Own arm (default):   python bench.py --gpus N --steps K --warmup W
     e2e    = same metric through the reference-facing C-ABI call xnart_render_frame with HOST
              buffers: the XnartFrame goes in, the frame comes back to pinned host memory inside the
              timed region.
-    roofline / cpu_baseline: see DESIGN.md ("Measurement").
+    roofline / cpu_baseline: see DESIGN.md ("Measurement").  "deep_scene" adds the same measurement for the
+             1M-triangle octree scene of BASELINE.json (N=1 only; not part of `value`).
 Reference arm:       python bench.py --impl reference ...
     times the CPU restatement of the reference (oracle, all host threads) on a bounded band of
     scanlines of the same frames.  The reference's own C# cannot be built here (no mono/dotnet).
@@ -99,19 +100,28 @@ def alg_flops(c):
     return 18 * c.nBox + 8 * c.nTriCulled + 51 * c.nTriFull + 120 * c.hits
 
 
-def cpu_baseline(scene, scenes, n_threads, rows, cam_index=0):
-    """Oracle (port of the reference's CPU path) on a band of scanlines; returns Mrays/s, seconds, rays."""
+def cpu_baseline(scene, scenes, n_threads, rows, cam_index=0, frames=1, budget_s=None, oracle=None):
+    """Oracle (port of the reference's CPU path) on `frames` frames (scanlines `rows` of each), stopping early
+    once `budget_s` seconds are spent; returns Mrays/s, seconds, rays, frames rendered."""
     from oracle import oracle as O
 
-    o = O.Oracle()
-    scenes.upload(o, scene)
-    f = scene.frame(W, H, camera=orbit_camera(scenes, cam_index))
-    t0 = time.perf_counter()
-    o.render_frame(f, n_threads=n_threads, rows=rows)
-    dt = time.perf_counter() - t0
-    rays = o.counters().rays
-    o.close()
-    return rays / dt / 1e6, dt, rays
+    o = oracle
+    if o is None:
+        o = O.Oracle()
+        scenes.upload(o, scene)
+    tot_t, tot_rays, done = 0.0, 0, 0
+    for k in range(frames):
+        f = scene.frame(W, H, camera=orbit_camera(scenes, cam_index + k))
+        t0 = time.perf_counter()
+        o.render_frame(f, n_threads=n_threads, rows=rows)
+        tot_t += time.perf_counter() - t0
+        tot_rays += o.counters().rays
+        done += 1
+        if budget_s is not None and tot_t >= budget_s:
+            break
+    if oracle is None:
+        o.close()
+    return tot_rays / tot_t / 1e6, tot_t, tot_rays, done
 
 
 def run_reference(args):
@@ -121,18 +131,26 @@ def run_reference(args):
         return 0
     from xna_ray_trace_b200 import scenes
 
+    from oracle import oracle as O
+
     scene = scenes.crate_scene()
     cores = os.cpu_count() or 1
-    rows = (H // 2 - 135, H // 2 + 135)  # 270 of 1080 scanlines through the crate: a bounded sample
+    # one step = FRAMES_PER_STEP whole 1080p frames (about half a second of work for all host threads),
+    # so that the default --steps/--warmup finish well within a few minutes
+    FRAMES_PER_STEP = 4
+    rows = (0, H)
+    o = O.Oracle()
+    scenes.upload(o, scene)
     for i in range(args.warmup):
-        cpu_baseline(scene, scenes, cores, (H // 2, H // 2 + 16), i)
+        cpu_baseline(scene, scenes, cores, rows, i, frames=1, oracle=o)
     tot_rays, tot_t = 0, 0.0
     for i in range(args.steps):
-        _, dt, rays = cpu_baseline(scene, scenes, cores, rows, i)
+        _, dt, rays, _ = cpu_baseline(scene, scenes, cores, rows, i * FRAMES_PER_STEP, frames=FRAMES_PER_STEP, oracle=o)
         tot_rays += rays
         tot_t += dt
+    o.close()
     v = tot_rays / tot_t / 1e6
-    frames_equiv = (rows[1] - rows[0]) / H
+    frames_equiv = float(FRAMES_PER_STEP)
     line = {
         "impl": "reference", "metric": "Mrays/s (primary+secondary)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
@@ -140,7 +158,7 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "width": W, "height": H, "max_reflections": 8,
                    "note": "reference C# cannot be built here (no mono/dotnet): CPU restatement (oracle) on host cores"},
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                         "sample": "scanlines %d..%d of each 1080p frame (%.0f%% of a frame), %d threads" % (rows[0], rows[1], 100 * frames_equiv, cores)},
+                         "sample": "%d whole 1080p frames per step (orbit cameras), %d threads, %.1f s in total" % (FRAMES_PER_STEP, cores, tot_t)},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": frames_equiv * args.steps / tot_t,
     }
@@ -155,6 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xnart", choices=["xnart", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-deep-scene", action="store_true", help="skip the secondary 1M-triangle measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -239,42 +258,96 @@ def main():
         x.render_frame(all_frames[i], out=pin)
     barrier()
     frames = all_frames[warm:]
-    t0 = time.perf_counter()
-    for f in frames:
-        x.render_frame(f, out=pin)
-    e2e_s = time.perf_counter() - t0
+    with ClockSampler(local_rank) as clocks2:
+        t0 = time.perf_counter()
+        for f in frames:
+            x.render_frame(f, out=pin)
+        e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_rays / float(te[0]) / 1e6
     checksum = int(pin.array.astype(np.uint64).sum())
+    clocks.rows += clocks2.rows  # both timed regions are short: pool their samples
 
-    # ---- roofline of the dominant kernel (k_level: trace + shade, D+1 launches per frame) ----------
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    # Shallow scenes render a frame in ONE cooperative launch (k_frame: all levels + resolve); its
+    # "levels" phase is timed on the device (global timer stamps).  Deep scenes: the persistent trace
+    # kernel k_trace, 2 launches per level.
     roof = None
     cpu = None
+    deep = None
     if rank == 0:
-        x.set_option(records.OPT_COUNTERS, 1)
-        x.render_frame_device(all_frames[warm], frame_dev.data_ptr(), None)
-        cc = x.counters()
-        x.set_option(records.OPT_COUNTERS, 0)
         peaks, how = measured_peaks()
-        n_launch = scene.max_reflections + 1
-        lvl = float(np.mean(lvl_ms)) * 1e-3  # seconds of k_level per frame, measured live with CUDA events
-        ab, af = alg_bytes(cc), alg_flops(cc)
-        achieved = ab / lvl / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": how, "kernel": "k_level<false>", "launches_per_step": n_launch,
-                "alg_bytes_per_launch": ab / n_launch, "avg_launch_ms": 1e3 * lvl / n_launch,
-                "alg_fp32_Tops": af / lvl / 1e12, "fp32_noFMA_peak_Tops_nominal": 148 * 128 * 1.965e9 / 1e12,
-                "k_level_share_of_step": float(np.mean(lvl_ms)) / (float(np.mean(lvl_ms)) + float(np.mean(res_ms)) + 1e-12)}
+        fp32_peak = 148 * 128 * 1.965e9 / 1e12
+
+        def roofline_of(xc, frame_list, kernel, launches_per_frame, traffic_key):
+            lv, rs = [], []
+            for f in frame_list:
+                xc.render_frame_device(f, frame_dev.data_ptr(), None)
+                c = xc.counters()
+                lv.append(c.msLevels); rs.append(c.msResolve)
+            xc.set_option(records.OPT_COUNTERS, 1)
+            xc.render_frame_device(frame_list[0], frame_dev.data_ptr(), None)
+            cc = xc.counters()
+            xc.set_option(records.OPT_COUNTERS, 0)
+            xc.render_frame_device(frame_list[0], frame_dev.data_ptr(), None)
+            lvl0 = xc.counters().msLevels * 1e-3  # same frame as the counters
+            ab, af = alg_bytes(cc), alg_flops(cc)
+            achieved = ab / lvl0 / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get(traffic_key)
+                except Exception:
+                    traffic = None
+            return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": traffic, "peak_source": how, "kernel": kernel, "launches_per_step": launches_per_frame,
+                    "alg_bytes_per_launch": ab / launches_per_frame, "avg_launch_ms": 1e3 * lvl0 / launches_per_frame,
+                    "alg_fp32_Tops": af / lvl0 / 1e12, "fp32_noFMA_peak_Tops_nominal": fp32_peak,
+                    "fp32_frac_of_noFMA_nominal": af / lvl0 / 1e12 / fp32_peak,
+                    "kernel_share_of_step": float(np.mean(lv)) / (float(np.mean(lv)) + float(np.mean(rs)) + 1e-12),
+                    "work_per_ray": {"slab_tests": cc.nBox / max(1, cc.rays), "triangle_refs": cc.nTriRef / max(1, cc.rays)},
+                    "note": "achieved = algorithmic bytes (SURVEY.md 8d, counted by the instrumented kernels == oracle) / device time of the "
+                            "kernel's trace phase; the scene is cache resident, so the FP32 view is reported beside it"}, float(np.mean(lv)) + float(np.mean(rs)), cc
+
+        roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_frame<false> (levels phase of the fused frame kernel)", 1, "k_frame")
+
+        if world == 1 and not args.no_deep_scene:
+            # second target of BASELINE.json's north_star: the 1M-triangle octree scene (configs[2] geometry) at 1080p
+            gs = scenes.grid_scene(707)
+            xg = capi.Xnart(devices=(local_rank,))
+            scenes.upload(xg, gs)
+            gframes = [gs.frame(W, H, camera=scenes.CameraData((np.sin(0.13 * i) * 80.0, 40.0, np.cos(0.13 * i) * 80.0), (0.0, 0.0, 0.0))) for i in range(6)]
+            for f in gframes[:2]:
+                xg.render_frame_device(f, frame_dev.data_ptr(), None)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            g0.record(stream)
+            for f in gframes:
+                xg.render_frame_device(f, frame_dev.data_ptr(), stream.cuda_stream)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1) / len(gframes)
+            grays = []
+            for f in gframes:
+                xg.render_frame_device(f, frame_dev.data_ptr(), None)
+                grays.append(xg.counters().rays)
+            groof, _, gcc = roofline_of(xg, gframes[:3], "k_trace<false> (persistent trace kernel, 2 launches per level)",
+                                        2 * (gs.max_reflections + 1), "k_trace")
+            deep = {"workload": "grid_1M_triangles_1080p_depth%d" % gs.max_reflections, "triangles": gs.n_triangles,
+                    "lights": len(gs.lights), "value": float(np.mean(grays)) / (gms * 1e-3) / 1e6, "unit": "Mrays/s",
+                    "ms_per_frame": gms, "frames_per_s": 1e3 / gms, "rays_per_frame": float(np.mean(grays)), "roofline": groof}
+            xg.close()
+
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rows = (H // 2 - 135, H // 2 + 135)
-            v_all, dt_all, _ = cpu_baseline(scene, scenes, cores, rows, warm)
-            v_one, dt_one, _ = cpu_baseline(scene, scenes, 1, (H // 2 - 34, H // 2 + 34), warm)
+            v_all, dt_all, _, n_all = cpu_baseline(scene, scenes, cores, (0, H), warm, frames=400, budget_s=10.0)
+            v_one, dt_one, _, n_one = cpu_baseline(scene, scenes, 1, (0, H), warm, frames=20, budget_s=4.0)
             cpu = {"value": v_all, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                   "sample": "scanlines %d..%d of one 1080p frame, %d threads, %.1f s" % (rows[0], rows[1], cores, dt_all),
-                   "single_thread_as_shipped": {"value": v_one, "cores": 1, "seconds": dt_one,
+                   "sample": "%d whole 1080p frames of the same workload (orbit cameras), %d threads, %.1f s" % (n_all, cores, dt_all),
+                   "single_thread_as_shipped": {"value": v_one, "cores": 1, "seconds": dt_one, "frames": n_one,
                                                 "note": "RayTracer.cs:99 hard-codes one worker"}}
 
     if rank == 0:
@@ -294,6 +367,7 @@ def main():
             "clocks": clocks.summary(),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "deep_scene": deep,
         }
         print(json.dumps(line))
     pin.free()

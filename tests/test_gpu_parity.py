@@ -229,3 +229,70 @@ def test_full_size_properties(X):
     assert np.array_equal(union, a)
     pin.free()
     x.close()
+
+
+def test_wavefront_equals_per_thread_at_full_size(X):
+    """BASELINE size, no oracle needed: the persistent-kernel schedule and the one-thread-per-ray
+    schedule are two executions of the same per-ray algorithm, so a 1080p frame of the 1M-triangle
+    grid (depth 4, 2 lights: 6.9 M rays through every phase of k_trace, including the cooperative
+    leaf tail) and the work counters must be identical."""
+    s = scenes.grid_scene(707)
+    x = X.Xnart()
+    scenes.upload(x, s)
+    f = s.frame(1920, 1080)
+    x.set_option(records.OPT_COUNTERS, 1)
+    x.set_option(records.OPT_TRAVERSAL, 2)
+    a = x.render_frame(f).copy()
+    ca = x.counters()
+    x.set_option(records.OPT_TRAVERSAL, 1)
+    b = x.render_frame(f)
+    cb = x.counters()
+    assert np.array_equal(a, b)
+    for k in ("raysShadow", "raysReflection", "hits", "nBox", "nTriRef", "nTriCulled", "nTriFull"):
+        assert getattr(ca, k) == getattr(cb, k), k
+    assert ca.hits > 1_000_000 and len(np.unique(a)) > 100  # a grey-scale scene
+    # determinism of the dynamic schedule: ray-to-lane assignment changes from run to run, pixels must not
+    x.set_option(records.OPT_COUNTERS, 0)
+    x.set_option(records.OPT_TRAVERSAL, 0)
+    c = x.render_frame(f).copy()
+    assert np.array_equal(a, c) and np.array_equal(c, x.render_frame(f))
+    x.close()
+
+
+@pytest.mark.parametrize("schedule", SCHEDULES)
+def test_tiles_chunks_and_odd_sizes(X, oracle_mod, schedule):
+    """8x4 pixel tiles (W % 8 == 0 and rows % 4 == 0), scanline order otherwise, and frames rendered in
+    several arena chunks all give the oracle's frame."""
+    s = make_scene("spheres")  # transparent: reflection + refraction queues, 4 objects sharing one mesh
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart()
+    x.set_option(records.OPT_TRAVERSAL, schedule)
+    scenes.upload(x, s)
+    for wh in ((96, 64), (100, 64), (96, 62), (101, 59)):
+        f = s.frame(*wh, max_reflections=3)
+        want = o.render_frame(f, n_threads=8)
+        assert np.array_equal(want, x.render_frame(f)), wh
+        x.set_option(records.OPT_ARENA_BYTES, 3_000_000)   # a few thousand pixels per chunk
+        assert np.array_equal(want, x.render_frame(f)), ("chunked", wh)
+        x.set_option(records.OPT_ARENA_BYTES, 8 << 30)
+    x.close()
+
+
+def test_render_frames_flythrough(X):
+    """xnart_render_frames == n calls of xnart_render_frame, into pageable and page-locked memory."""
+    s = make_scene("crate")
+    x = X.Xnart()
+    scenes.upload(x, s)
+    import math
+    frames = [s.frame(320, 180, camera=scenes.CameraData((math.sin(0.4 * i) * 72.0, 35.0, math.cos(0.4 * i) * 72.0), (0.0, 11.8, 0.0)))
+              for i in range(7)]
+    single = np.stack([x.render_frame(f).copy() for f in frames])
+    assert len({a.tobytes() for a in single}) == 7
+    got = x.render_frames(frames)
+    assert np.array_equal(single, got)
+    assert x.counters().raysPrimary == 7 * 320 * 180
+    pin = X.PinnedFrame(180, 320, frames=7)
+    assert np.array_equal(single, x.render_frames(frames, out=pin.array))
+    pin.free()
+    x.close()
