@@ -149,12 +149,14 @@ struct DevArena {
     unsigned long long* counters;  // kCounterSlots
     unsigned int nodeCapacity, rayCapacity;
     unsigned int* overflow;
-    // wavefront path (deep scenes): closest hits of the level's rays, and the shadow-ray batch of the level
-    int4* hit;           // 2 per ray slot of the level
-    float4* shO;         // nLights segments of rayCapacity slots: (hit position, distance to the light)
-    float4* shD;
-    int2* shIgn;
-    int4* shHit;         // 2 per shadow slot
+    // wavefront path (deep scenes): closest hits of the level's rays, and the shadow-ray batch of the level.
+    // Double buffered by level parity: the shadow batch + shade B of level L run on a side stream while
+    // the main stream already traces level L+1.
+    int4* hit[2];        // 2 per ray slot of the level
+    float4* shO[2];      // nLights segments of rayCapacity slots: (hit position, distance to the light)
+    float4* shD[2];
+    int2* shIgn[2];
+    int4* shHit[2];      // 2 per shadow slot
     unsigned int* shadowHits;   // [maxLevels+2] hits per level (= rays per shadow segment)
     unsigned int* fetch;        // [2*(maxLevels+2)] work counters of the trace launches
 };

@@ -134,36 +134,34 @@ __device__ __forceinline__ unsigned appendRay(const DevArena& A, int level, int 
     return child;
 }
 
-// Everything CastRay does after the light loop (:545-727): surface colour, the path node, and the
-// reflection / refraction rays of the next level.
-__device__ __forceinline__ void finishHit(const DevScene& S, const DevFrame& F, const DevArena& A, int level, bool last, unsigned node,
-                                          unsigned nextBase, const Hit& h0, const DevMesh* __restrict__ M, int triG, V3 N,
-                                          V3 lightResult, V3 rd0, float refIndex, unsigned& nRefl, unsigned& nRefr) {
+// Surface colour of a hit (:568-581): texture lookup at the interpolated uv, or the triangle colour.
+// alphaW receives triangle.color.W.
+__device__ __forceinline__ V3 surfaceColor(const DevScene& S, const DevFrame& F, const DevMesh* __restrict__ M, int triG, float u, float v,
+                                           float& alphaW) {
     const float4* __restrict__ T = S.triS + 5 * (size_t)triG;
-    V3 surf;
     float4 s3 = __ldg(&T[3]), s4 = __ldg(&T[4]);
+    alphaW = s4.z;
     if (M->flags & MESH_USE_TEXTURE) {  // :568-575
         float4 s0 = __ldg(&T[0]), s1 = __ldg(&T[1]);
         float ax = s0.z - s0.x, ay = s0.w - s0.y;  // uv2 - uv1
         float bx = s1.x - s0.x, by = s1.y - s0.y;  // uv3 - uv1
-        float tu = (s0.x + (ax * h0.u)) + (bx * h0.v);
-        float tv = (s0.y + (ay * h0.u)) + (by * h0.v);
-        surf = lookupUV(S.texels + M->texOffset, M->texW, M->texH, tu, tv, F.addressMode, F.filtering);
-    } else {
-        surf = mk(s3.w, s4.x, s4.y);
+        float tu = (s0.x + (ax * u)) + (bx * v);
+        float tv = (s0.y + (ay * u)) + (by * v);
+        return lookupUV(S.texels + M->texOffset, M->texW, M->texH, tu, tv, F.addressMode, F.filtering);
     }
-    if (last) {
-        A.color[node] = packColor(mulv(lightResult, surf), F.semantics);  // :726
-        A.flags[node] = 0u;
-        return;
-    }
+    return mk(s3.w, s4.x, s4.y);
+}
+
+// The reflection and refraction rays of a hit (:547-559, :656-698), appended to the next level's
+// queue; returns the path-node indices of the two children (refraction: 0xFFFFFFFF when none).
+__device__ __forceinline__ uint2 emitChildren(const DevScene& S, const DevArena& A, int level, unsigned nextBase, const Hit& h0,
+                                              const DevMesh* __restrict__ M, V3 N, V3 rd0, float refIndex, unsigned& nRefl, unsigned& nRefr) {
     const int outq = (level & 1) ^ 1;
     // reflection ray (:547-559) — always cast, whatever the reflectiveness (Q9)
     V3 rdir = normalize(reflect(rd0, N));
     unsigned reflChild = appendRay(A, level, outq, nextBase, h0.pos, rdir, refIndex, h0.mesh, h0.tri);
     unsigned refrChild = 0xFFFFFFFFu;
     nRefl++;
-    const float alphaW = s4.z;  // triangle.color.W
     if (M->flags & MESH_TRANSPARENT) {
         // refraction (:656-698), double-precision island for the Snell term
         float n1, n2;
@@ -178,9 +176,25 @@ __device__ __forceinline__ void finishHit(const DevScene& S, const DevFrame& F, 
         refrChild = appendRay(A, level, outq, nextBase, h0.pos, normalize(refr), n2, h0.mesh, h0.tri);
         nRefr++;
     }
+    return make_uint2(reflChild, refrChild);
+}
+
+// Everything CastRay does after the light loop (:545-727): surface colour, the path node, and the
+// reflection / refraction rays of the next level.
+__device__ __forceinline__ void finishHit(const DevScene& S, const DevFrame& F, const DevArena& A, int level, bool last, unsigned node,
+                                          unsigned nextBase, const Hit& h0, const DevMesh* __restrict__ M, int triG, V3 N,
+                                          V3 lightResult, V3 rd0, float refIndex, unsigned& nRefl, unsigned& nRefr) {
+    float alphaW;
+    const V3 surf = surfaceColor(S, F, M, triG, h0.u, h0.v, alphaW);
+    if (last) {
+        A.color[node] = packColor(mulv(lightResult, surf), F.semantics);  // :726
+        A.flags[node] = 0u;
+        return;
+    }
+    const uint2 ch = emitChildren(S, A, level, nextBase, h0, M, N, rd0, refIndex, nRefl, nRefr);
     A.nodeA[node] = make_float4(lightResult.x, lightResult.y, lightResult.z, M->oneMinusReflectiveness);
     A.nodeB[node] = make_float4(surf.x, surf.y, surf.z, alphaW);
-    A.nodeC[node] = make_uint2(reflChild, refrChild);
+    A.nodeC[node] = ch;
     A.flags[node] = 1u;
 }
 

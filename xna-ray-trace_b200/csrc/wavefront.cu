@@ -9,11 +9,14 @@
 //
 //   level L:  k_gen_primary (L = 0)      RayTracer.Render's Unproject pair (RayTracer.cs:410-421) -> ray queue
 //             k_trace      (level rays)  OctreeSpatialManager / MeshOctree.GetRayIntersection (RayTracer.cs:512)
-//             k_shade_a                  hit position, fragment normal (:520-531), shadow rays (:467-482)
-//             k_trace      (shadow rays) IsLightPathObstructed's query (:485), nLights segments
-//             k_shade_b                  light sum (:535-542), surface colour, reflection / refraction rays of
-//                                        level L+1 (:545-702), path node
+//             k_shade_a                  hit position, fragment normal (:520-531), shadow rays (:467-482) and
+//                                        the reflection / refraction rays of level L+1 (:545-702)
+//       side: k_trace      (shadow rays) IsLightPathObstructed's query (:485), nLights segments
+//       side: k_shade_b                  light sum (:535-542), surface colour, path node
 //   then k_resolve (kernels.cu) bottom-up, as in the per-thread path.
+// The rays of level L+1 depend on the hits of level L only, not on its shadow verdicts, so the shadow
+// batch and shade B of a level run on a side stream while the main stream already traces the next
+// level: the serial tail of one batch (a few grazing rays) overlaps the bulk of the other.
 //
 // k_trace: persistent warps; per lane a small state machine (idle -> pick the next (object, mesh)
 // pair -> walk its octree, alternating descend and leaf steps (trace.cuh) -> merge -> next pair ->
@@ -219,11 +222,15 @@ __device__ __forceinline__ Hit hitOf(const DevScene& S, const int4 a, const int4
 __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     const unsigned count = A.levelCount[level];
     const unsigned base = A.levelBase[level];
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.levelBase[level + 1] = base + count;
-    unsigned nHits = 0;
+    const unsigned nextBase = base + count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.levelBase[level + 1] = nextBase;
+    const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
+    const int par = level & 1;
+    const int4* __restrict__ hit = A.hit[par];
+    unsigned nHits = 0, nRefl = 0, nRefr = 0;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
-        const int4 ha = A.hit[2 * (size_t)idx], hb = A.hit[2 * (size_t)idx + 1];
+        const int4 ha = hit[2 * (size_t)idx], hb = hit[2 * (size_t)idx + 1];
         if (ha.x < 0) {
             A.color[node] = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);  // RayTracer.cs:732
             A.flags[node] = 0u;
@@ -239,38 +246,52 @@ __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevAren
         const DevMesh* __restrict__ M = &S.meshes[h.mesh];
         const V3 N = fragmentNormal(S, M, M->triBase + h.tri, h);
         // compact hit index: the shadow rays of hit k sit at slot q*rayCapacity + k, one segment per light
-        cg::coalesced_group g = cg::coalesced_threads();
-        unsigned b0 = 0;
-        if (g.thread_rank() == 0) b0 = atomicAdd(&A.shadowHits[level], g.size());
-        const unsigned k = g.shfl(b0, 0) + g.thread_rank();
+        unsigned k;
+        {
+            cg::coalesced_group g = cg::coalesced_threads();
+            unsigned b0 = 0;
+            if (g.thread_rank() == 0) b0 = atomicAdd(&A.shadowHits[level], g.size());
+            k = g.shfl(b0, 0) + g.thread_rank();
+        }
         for (int q = 0; q < F.nLights; q++) {
             float distToLight;
             const V3 sd = shadowDir(lights[q], h.pos, distToLight);
             const size_t s = (size_t)q * A.rayCapacity + k;
-            A.shO[s] = make_float4(h.pos.x, h.pos.y, h.pos.z, distToLight);
-            A.shD[s] = make_float4(sd.x, sd.y, sd.z, 0.0f);
-            A.shIgn[s] = make_int2(h.mesh, h.tri);
+            A.shO[par][s] = make_float4(h.pos.x, h.pos.y, h.pos.z, distToLight);
+            A.shD[par][s] = make_float4(sd.x, sd.y, sd.z, 0.0f);
+            A.shIgn[par][s] = make_int2(h.mesh, h.tri);
+        }
+        // the rays of the next level depend on the hit alone (:547-559, :656-698): emitted here, so the next
+        // level can be traced while this level's shadow batch is still running
+        if (!last) {
+            const float4 o4 = A.rayO[par][idx], d4 = A.rayD[par][idx];
+            A.nodeC[node] = emitChildren(S, A, level, nextBase, h, M, N, mk(d4.x, d4.y, d4.z), o4.w, nRefl, nRefr);
         }
         A.nodeA[node] = make_float4(h.pos.x, h.pos.y, h.pos.z, __uint_as_float(k));
         A.nodeB[node] = make_float4(N.x, N.y, N.z, 0.0f);
     }
-    const unsigned sH = warpSum(nHits);
-    if ((threadIdx.x & 31u) == 0 && sH) atomicAdd(&A.counters[CTR_HITS], (unsigned long long)sH);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned sH = warpSum(nHits), sR = warpSum(nRefl), sF = warpSum(nRefr);
+    if (lane == 0) {
+        if (sH) atomicAdd(&A.counters[CTR_HITS], (unsigned long long)sH);
+        if (sR) atomicAdd(&A.counters[CTR_RAYS_REFLECTION], (unsigned long long)sR);
+        if (sF) atomicAdd(&A.counters[CTR_RAYS_REFRACTION], (unsigned long long)sF);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// shade B: shadow verdicts -> light sum, surface colour, next-level rays, path node
+// shade B: shadow verdicts -> light sum (:535-542), surface colour, path node (:584, :705-727)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_shade_b(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     const unsigned count = A.levelCount[level];
     const unsigned base = A.levelBase[level];
-    const unsigned nextBase = base + count;
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
-    const int in = level & 1;
-    unsigned nRefl = 0, nRefr = 0;
+    const int par = level & 1;
+    const int4* __restrict__ hit = A.hit[par];
+    const int4* __restrict__ shHit = A.shHit[par];
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
-        const int4 ha = A.hit[2 * (size_t)idx], hb = A.hit[2 * (size_t)idx + 1];
+        const int4 ha = hit[2 * (size_t)idx], hb = hit[2 * (size_t)idx + 1];
         if (ha.x < 0) continue;
         Hit h = hitOf(S, ha, hb);
         const float4 pa = A.nodeA[node], nb = A.nodeB[node];
@@ -280,19 +301,21 @@ __global__ void __launch_bounds__(256) k_shade_b(DevScene S, DevFrame F, DevAren
         V3 lightResult = mk(0.0f, 0.0f, 0.0f);
         for (int q = 0; q < F.nLights; q++) {
             const size_t s = (size_t)q * A.rayCapacity + k;
-            const int4 sa = A.shHit[2 * s], sb = A.shHit[2 * s + 1];
+            const int4 sa = shHit[2 * s], sb = shHit[2 * s + 1];
             const Hit sh = hitOf(S, sa, sb);
-            lightResult = addLight(S, lights[q], sa.x >= 0, sh, A.shO[s].w, h.pos, N, lightResult);
+            lightResult = addLight(S, lights[q], sa.x >= 0, sh, A.shO[par][s].w, h.pos, N, lightResult);
         }
         const DevMesh* __restrict__ M = &S.meshes[h.mesh];
-        const float4 o4 = A.rayO[in][idx], d4 = A.rayD[in][idx];
-        finishHit(S, F, A, level, last, node, nextBase, h, M, M->triBase + h.tri, N, lightResult, mk(d4.x, d4.y, d4.z), o4.w, nRefl, nRefr);
-    }
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned sR = warpSum(nRefl), sF = warpSum(nRefr);
-    if (lane == 0) {
-        if (sR) atomicAdd(&A.counters[CTR_RAYS_REFLECTION], (unsigned long long)sR);
-        if (sF) atomicAdd(&A.counters[CTR_RAYS_REFRACTION], (unsigned long long)sF);
+        float alphaW;
+        const V3 surf = surfaceColor(S, F, M, M->triBase + h.tri, h.u, h.v, alphaW);
+        if (last) {
+            A.color[node] = packColor(mulv(lightResult, surf), F.semantics);  // :726
+            A.flags[node] = 0u;
+        } else {
+            A.nodeA[node] = make_float4(lightResult.x, lightResult.y, lightResult.z, M->oneMinusReflectiveness);
+            A.nodeB[node] = make_float4(surf.x, surf.y, surf.z, alphaW);
+            A.flags[node] = 1u;
+        }
     }
 }
 

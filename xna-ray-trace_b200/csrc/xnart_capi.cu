@@ -43,6 +43,8 @@ struct DeviceState {
     int traceBlocks = 0, traceBlocksCount = 0;  // resident grid of the persistent trace kernel
     int2* pairs = nullptr;
     bool lastWave = false;
+    cudaStream_t sideStream = nullptr;                 // shadow batch + shade B of a level (wavefront path)
+    std::vector<cudaEvent_t> evA, evB;                  // per level: shade A done (main) / shade B done (side)
     bool lastFused = false;
     // output
     uint32_t* frameBuf = nullptr; size_t frameBufPixels = 0;
@@ -86,6 +88,7 @@ struct XnartCtx {
     bool countKernels = false;
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
+    bool overlapLevels = true;  // XNART_OPT_OVERLAP_LEVELS: side stream for the shadow batches of the wavefront path
     bool fuseFrame = true;   // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
@@ -159,6 +162,10 @@ int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds)
             cudaDeviceGetAttribute(&d.smCount, cudaDevAttrMultiProcessorCount, id);
             for (auto& ev : d.ev) cudaEventCreate(&ev);
             cudaStreamCreateWithFlags(&d.copyStream, cudaStreamNonBlocking);
+            cudaStreamCreateWithFlags(&d.sideStream, cudaStreamNonBlocking);
+            d.evA.resize(kMaxLevels + 2); d.evB.resize(kMaxLevels + 2);
+            for (auto& e : d.evA) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            for (auto& e : d.evB) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
             for (int k = 0; k < 2; k++) {
                 cudaEventCreateWithFlags(&d.evRendered[k], cudaEventDisableTiming);
                 cudaEventCreateWithFlags(&d.evCopied[k], cudaEventDisableTiming);
@@ -189,6 +196,9 @@ int32_t xnart_destroy(XnartCtx* c) {
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; k++) { if (d.evRendered[k]) cudaEventDestroy(d.evRendered[k]); if (d.evCopied[k]) cudaEventDestroy(d.evCopied[k]); }
         if (d.copyStream) cudaStreamDestroy(d.copyStream);
+        if (d.sideStream) { cudaStreamSynchronize(d.sideStream); cudaStreamDestroy(d.sideStream); }
+        for (auto& e : d.evA) if (e) cudaEventDestroy(e);
+        for (auto& e : d.evB) if (e) cudaEventDestroy(e);
         cudaFree(d.frameBuf2);
         cudaStreamDestroy(d.stream);
     }
@@ -207,6 +217,7 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
             if (value != XNART_SEMANTICS_XNA40) return fail(c, XNART_ERR_UNSUPPORTED, "only XNA 4.0 slab semantics are implemented on the device");
             c->traceSemantics = (int)value; return XNART_OK;
         case XNART_OPT_FUSE_FRAME: c->fuseFrame = value != 0; return XNART_OK;
+        case XNART_OPT_OVERLAP_LEVELS: c->overlapLevels = value != 0; return XNART_OK;
         case XNART_OPT_TRAVERSAL:
             if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
             c->traversalMode = (int)value; return XNART_OK;
@@ -464,7 +475,7 @@ static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned ray
     const size_t shRays = wave ? (size_t)rays * (size_t)std::max(nLights, 1) : 0;
     size_t need = al((size_t)nodes * 16) * 2 + al((size_t)nodes * 8) + al((size_t)nodes * 4) * 2 +
                   2 * (al((size_t)rays * 16) * 2 + al((size_t)rays * 8));
-    if (wave) need += al((size_t)rays * 32) + al(shRays * 16) * 2 + al(shRays * 8) + al(shRays * 32);
+    if (wave) need += 2 * (al((size_t)rays * 32) + al(shRays * 16) * 2 + al(shRays * 8) + al(shRays * 32));
     if (need > d.arenaBytes) {
         CU_TRY(c, cudaStreamSynchronize(d.stream));
         cudaFree(d.arenaBlock);
@@ -485,13 +496,15 @@ static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned ray
         A.rayD[q] = (float4*)take((size_t)rays * 16);
         A.rayIgn[q] = (int2*)take((size_t)rays * 8);
     }
-    A.hit = nullptr; A.shO = A.shD = nullptr; A.shIgn = nullptr; A.shHit = nullptr;
-    if (wave) {
-        A.hit = (int4*)take((size_t)rays * 32);
-        A.shO = (float4*)take(shRays * 16);
-        A.shD = (float4*)take(shRays * 16);
-        A.shIgn = (int2*)take(shRays * 8);
-        A.shHit = (int4*)take(shRays * 32);
+    for (int q = 0; q < 2; q++) {
+        A.hit[q] = nullptr; A.shO[q] = A.shD[q] = nullptr; A.shIgn[q] = nullptr; A.shHit[q] = nullptr;
+        if (wave) {
+            A.hit[q] = (int4*)take((size_t)rays * 32);
+            A.shO[q] = (float4*)take(shRays * 16);
+            A.shD[q] = (float4*)take(shRays * 16);
+            A.shIgn[q] = (int2*)take(shRays * 8);
+            A.shHit[q] = (int4*)take(shRays * 32);
+        }
     }
     A.levelCount = d.levelWords;
     A.levelBase = d.levelWords + (kMaxLevels + 2);
@@ -559,7 +572,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     const double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
     const double raysPerPixel = c->hasTransparent ? std::ldexp(1.0, D) : 1.0;
     const bool wave = useWave(c, d);
-    const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * (80.0 + (wave ? 32.0 + 72.0 * std::max(F.nLights, 1) : 0.0)) + 64.0;
+    const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * (80.0 + (wave ? 2.0 * (32.0 + 72.0 * std::max(F.nLights, 1)) : 0.0)) + 64.0;
     long long chunk = (long long)std::floor((double)c->arenaLimit / bytesPerPixel);
     chunk = std::min<long long>(chunk, (long long)(4.0e9 / nodesPerPixel));
     chunk = std::min(chunk, localPixels);
@@ -607,26 +620,38 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
                 c->launches++;
                 continue;
             }
-            // wavefront: [primary rays] -> trace -> shade A (shadow rays) -> trace -> shade B (next level's rays)
+            // wavefront, main stream: [primary rays] -> trace -> shade A (shadow rays + next level's rays);
+            // side stream: shadow trace -> shade B, overlapping the next level on the main stream
             const DevArena& A = d.arena;
             const int tb = c->countKernels ? d.traceBlocksCount : d.traceBlocks;
             if (L == 0) { CU_TRY(c, launchGenPrimary(F, A, maxBlocks, st)); c->launches++; }
             const int in = L & 1;
+            // hit / shadow buffers of this parity were last used by level L-2: its shade B must be done
+            if (L >= 2) CU_TRY(c, cudaStreamWaitEvent(st, d.evB[L - 2], 0));
             TraceJob J;
-            J.rayO = A.rayO[in]; J.rayD = A.rayD[in]; J.rayIgn = A.rayIgn[in]; J.out = A.hit;
+            J.rayO = A.rayO[in]; J.rayD = A.rayD[in]; J.rayIgn = A.rayIgn[in]; J.out = A.hit[in];
             J.segCount = &A.levelCount[L]; J.fetch = &A.fetch[2 * L]; J.nSeg = 1; J.segStride = 0;
             CU_TRY(c, launchTrace(d.scene, J, d.counters, tb, c->countKernels, st));
             CU_TRY(c, launchShadeA(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, st));
             c->launches += 2;
+            CU_TRY(c, cudaEventRecord(d.evA[L], st));
+            cudaStream_t ss = c->overlapLevels ? d.sideStream : st;
+            if (ss != st) CU_TRY(c, cudaStreamWaitEvent(ss, d.evA[L], 0));
             if (F.nLights > 0) {
                 TraceJob Sj;
-                Sj.rayO = A.shO; Sj.rayD = A.shD; Sj.rayIgn = A.shIgn; Sj.out = A.shHit;
+                Sj.rayO = A.shO[in]; Sj.rayD = A.shD[in]; Sj.rayIgn = A.shIgn[in]; Sj.out = A.shHit[in];
                 Sj.segCount = &A.shadowHits[L]; Sj.fetch = &A.fetch[2 * L + 1]; Sj.nSeg = (unsigned)F.nLights; Sj.segStride = A.rayCapacity;
-                CU_TRY(c, launchTrace(d.scene, Sj, d.counters, tb, c->countKernels, st));
+                CU_TRY(c, launchTrace(d.scene, Sj, d.counters, tb, c->countKernels, ss));
                 c->launches++;
             }
-            CU_TRY(c, launchShadeB(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, st));
+            CU_TRY(c, launchShadeB(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, ss));
             c->launches++;
+            CU_TRY(c, cudaEventRecord(d.evB[L], ss));
+            if (L == D) {
+                // the resolve needs every shade B (the side stream runs them in order)
+                CU_TRY(c, cudaStreamWaitEvent(st, d.evB[L], 0));
+                if (L >= 1) CU_TRY(c, cudaStreamWaitEvent(st, d.evB[L - 1], 0));
+            }
         }
         if (p0 == 0) CU_TRY(c, cudaEventRecord(d.ev[1], st));
         for (int L = D - 1; L >= 0; L--) {
