@@ -296,3 +296,25 @@ def test_render_frames_flythrough(X):
     assert np.array_equal(single, x.render_frames(frames, out=pin.array))
     pin.free()
     x.close()
+
+
+def test_flythrough_into_avi_sink(X, tmp_path):
+    """configs[3] in miniature: orbit frames through xnart_render_frames into the AviManager-style sink;
+    what comes back out of the file equals what xnart_render_frame renders."""
+    from xna_ray_trace_b200 import avi, flythrough
+
+    s = make_scene("grid")
+    x = X.Xnart()
+    scenes.upload(x, s)
+    cams = flythrough.orbit_cameras(6, radius=14.0, height_y=6.0)
+    path = str(tmp_path / "fly.avi")
+    mgr = avi.AviManager(path, False)
+    sink = mgr.AddVideoStream(False, 30, 0, 160, 96, avi.PIXELFORMAT_24BPP_RGB)
+    n, rays, _ = flythrough.render_flythrough(x, s, cams, 160, 96, sink=sink, batch=4)
+    mgr.Close()
+    assert n == 6 and rays > 6 * 160 * 96
+    v = avi.AviManager(path, True).GetVideoStream()
+    assert v.CountFrames == 6
+    for i in (0, 3, 5):
+        assert np.array_equal(v.GetBitmap(i), x.render_frame(s.frame(160, 96, camera=cams[i])))
+    x.close()

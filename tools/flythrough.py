@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""tools/flythrough.py — BASELINE.json configs[3]: an N-frame 1080p orbit of the 1M-triangle scene, frames
+sharded across the GPUs of the box, gathered to rank 0 and written through the AviManager-style sink.
+
+  python tools/flythrough.py --frames 600 --out /tmp/fly.avi
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/flythrough.py --frames 600
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="grid", choices=["grid", "crate", "soup"])
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--frames", type=int, default=600)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--fps", type=float, default=30.0)   # Game1.cs:198
+    ap.add_argument("--out", default=None, help="AVI file written by rank 0 (omit to discard the frames)")
+    args = ap.parse_args()
+
+    import torch
+
+    from xna_ray_trace_b200 import avi, capi, flythrough, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+    if args.scene == "grid":
+        s = scenes.grid_scene(args.n or 707)
+        cams = flythrough.orbit_cameras(args.frames)
+    elif args.scene == "soup":
+        s = scenes.soup_scene(args.n or 1_000_000)
+        cams = flythrough.orbit_cameras(args.frames, radius=250.0, height_y=0.0)
+    else:
+        s = scenes.crate_scene()
+        cams = flythrough.orbit_cameras(args.frames, radius=72.0, height_y=35.0, target=(0.0, 11.8, 0.0))
+    x = capi.Xnart(devices=(local,))
+    scenes.upload(x, s)
+    sink, mgr = None, None
+    if rank == 0 and args.out:
+        mgr = avi.AviManager(args.out, False)
+        sink = mgr.AddVideoStream(False, args.fps, 0, args.width, args.height, avi.PIXELFORMAT_24BPP_RGB)
+    x.render_frames([s.frame(args.width, args.height, camera=cams[0])])  # warm-up
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_mine, rays, secs = flythrough.render_flythrough(x, s, cams, args.width, args.height, sink=sink, world=world, rank=rank, device=dev)
+    if world > 1:
+        tot = torch.tensor([float(rays)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        rays = float(tot[0])
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    if mgr is not None:
+        mgr.Close()
+    if rank == 0:
+        print(json.dumps({"workload": "%s flythrough %dx%d" % (s.name, args.width, args.height), "frames": args.frames, "n_gpus": world,
+                          "wall_s": wall, "frames_per_s": args.frames / wall, "Mrays_per_s": rays / wall / 1e6,
+                          "render_s_rank0": secs, "avi": args.out, "avi_bytes": os.path.getsize(args.out) if args.out else None}))
+    x.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
