@@ -198,32 +198,52 @@ def main():
     scene = scenes.crate_scene()
     x = capi.Xnart(devices=(local_rank,))
     scenes.upload(x, scene)
+    if os.environ.get("XNART_BENCH_FUSE") is not None:  # experiment switch: 0 = one launch per level instead of k_frame
+        x.set_option(records.OPT_FUSE_FRAME, int(os.environ["XNART_BENCH_FUSE"]))
 
-    # two frame buffers: the NCCL gather of frame i (async, on NCCL's stream) overlaps the rendering of frame i+1
-    frame_bufs = [torch.zeros((H, W), dtype=torch.int32, device=dev) for _ in range(2)]
-    frame_dev = frame_bufs[0]
-    gathered = [[torch.zeros((H, W), dtype=torch.int32, device=dev) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    # Frames are rendered into a ring of 2 x GROUP device buffers; every GROUP steps ONE async NCCL gather
+    # ships the last GROUP frames of every rank to rank 0 (on NCCL's stream) while the next group is being
+    # rendered.  Grouping keeps the host-side cost of the collective (one Python/NCCL call) off the
+    # critical path: a 1080p crate frame takes only ~0.6 ms of GPU time.
+    GROUP = 4 if world > 1 else 1
+    ring = torch.zeros((2, GROUP, H, W), dtype=torch.int32, device=dev)
+    frame_dev = ring[0, 0]
+    gathered = [[torch.zeros((GROUP, H, W), dtype=torch.int32, device=dev) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     pending = [None, None]
     stream = torch.cuda.current_stream()
 
     warm = max(args.warmup, 3)
     # camera matrices are host-side inputs (Camera.View/Projection in the reference): built up front
     all_frames = [scene.frame(W, H, camera=orbit_camera(scenes, i * world + rank)) for i in range(warm + args.steps)]
+    state = {"n": 0}
+
+    def flush_group(half):
+        if world > 1:
+            pending[half] = dist.gather(ring[half], gathered[half], dst=0, async_op=True)
 
     def step(i):
-        b = i & 1
-        if pending[b] is not None:
-            pending[b].wait()   # the render stream waits until this buffer's previous gather has finished
-            pending[b] = None
-        x.render_frame_device(all_frames[i], frame_bufs[b].data_ptr(), stream.cuda_stream)
-        if world > 1:
-            pending[b] = dist.gather(frame_bufs[b], gathered[b], dst=0, async_op=True)
+        k = state["n"]
+        half, slot = (k // GROUP) & 1, k % GROUP
+        if slot == 0 and pending[half] is not None:
+            pending[half].wait()   # the render stream waits until this half's previous gather has finished
+            pending[half] = None
+        x.render_frame_device(all_frames[i], ring[half, slot].data_ptr(), stream.cuda_stream)
+        state["n"] = k + 1
+        if slot == GROUP - 1:
+            flush_group(half)
 
-    def barrier():
+    def drain():
+        k = state["n"]
+        if world > 1 and k % GROUP != 0:      # a partial group: ship it as it is (stale tail slots are ignored)
+            flush_group((k // GROUP) & 1)
+            state["n"] = k + (GROUP - k % GROUP)
         for b in range(2):
             if pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
+
+    def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -239,10 +259,7 @@ def main():
         ev0.record(stream)
         for i in range(args.steps):
             step(warm + i)
-        for b in range(2):   # the last gathers belong to the timed region
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+        drain()              # the last gathers belong to the timed region
         ev1.record(stream)
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -286,9 +303,9 @@ def main():
     clocks.rows += clocks2.rows  # both timed regions are short: pool their samples
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
-    # Shallow scenes render a frame in ONE cooperative launch (k_frame: all levels + resolve); its
-    # "levels" phase is timed on the device (global timer stamps).  Deep scenes: the persistent trace
-    # kernel k_trace, 2 launches per level.
+    # Shallow scenes: k_level, one launch per recursion level (D+1 per frame) + the resolve launches; the levels
+    # are timed on the device with CUDA events on the launching stream (XnartCounters.msLevels).  Deep scenes:
+    # the persistent trace kernel k_trace, 2 launches per level.
     roof = None
     cpu = None
     deep = None
@@ -327,7 +344,11 @@ def main():
                     "note": "achieved = algorithmic bytes (SURVEY.md 8d, counted by the instrumented kernels == oracle) / device time of the "
                             "kernel's trace phase; the scene is cache resident, so the FP32 view is reported beside it"}, float(np.mean(lv)) + float(np.mean(rs)), cc
 
-        roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_frame<false> (levels phase of the fused frame kernel)", 1, "k_frame")
+        if os.environ.get("XNART_BENCH_FUSE") == "1":
+            roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_frame<false> (levels phase of the fused frame kernel)", 1, "k_frame")
+        else:
+            roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_level<false, 2> (one launch per recursion level)",
+                                     scene.max_reflections + 1, "k_level")
 
         if world == 1 and not args.no_deep_scene:
             # second target of BASELINE.json's north_star: the 1M-triangle octree scene (configs[2] geometry) at 1080p
@@ -372,7 +393,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "max_reflections": scene.max_reflections,
                        "triangles": scene.n_triangles, "lights": len(scene.lights), "frames_per_step_per_gpu": 1,
-                       "parallelism": "frames sharded across GPUs (one per GPU per step), async NCCL gather to rank 0 overlapping the next frame" if world > 1 else "single GPU",
+                       "parallelism": "frames sharded across GPUs (one per GPU per step), async NCCL gather to rank 0 every %d steps, overlapping the next frames" % GROUP if world > 1 else "single GPU",
                        "l2": "per-frame path arena (~0.9 GB) exceeds L2; a different camera every step"},
             "frames_per_s": world * args.steps / (ms * 1e-3),
             "rays_per_frame": total_rays / (world * max(1, args.steps)),

@@ -114,7 +114,7 @@ enum {
     XNART_OPT_ARENA_BYTES = 2,   /* upper bound for the per-render path arena (default 8 GiB) */
     XNART_OPT_SEMANTICS = 3,     /* default semantics for xnart_trace_rays */
     XNART_OPT_TRAVERSAL = 4,     /* kernel schedule: 0 auto, 1 one thread per ray, 2 wavefront (persistent trace kernel) */
-    XNART_OPT_FUSE_FRAME = 5,    /* 0/1 (default 1): shallow scenes render a frame in one cooperative launch */
+    XNART_OPT_FUSE_FRAME = 5,    /* 0/1 (default 0): shallow scenes render a frame in one cooperative launch */
     XNART_OPT_OVERLAP_LEVELS = 6 /* 0/1 (default 1): wavefront path runs a level's shadow batch beside the next level */
 };
 

@@ -21,6 +21,9 @@
 #ifndef XN_LEVEL_MIN_BLOCKS
 #define XN_LEVEL_MIN_BLOCKS 2
 #endif
+#ifndef XN_LEAF_MIN_BLOCKS
+#define XN_LEAF_MIN_BLOCKS 3
+#endif
 #ifndef XN_DEEP_MIN_BLOCKS
 #define XN_DEEP_MIN_BLOCKS 4
 #endif
@@ -33,7 +36,7 @@ namespace xn {
 // MINB = resident blocks per SM the register allocation is sized for: 2 (128 registers) suits
 // leaf-sized meshes where the kernel is issue bound; 4 (64 registers, some spilling) suits deep
 // octrees, where the walk is bound by dependent-load latency and more resident warps hide it.
-template <bool COUNT>
+template <bool COUNT, bool LEAFONLY>
 __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* __restrict__ lights,
                                           int level, Ctr& ctr, unsigned& nHits, unsigned& nRefl, unsigned& nRefr) {
     unsigned count, base;
@@ -56,7 +59,7 @@ __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, 
         int triG = 0;
         for (int q = 0;; q++) {
             Hit h;
-            bool ok = traceScene<COUNT>(S, qo, qd, qm, qt, h, ctr);
+            bool ok = traceScene<COUNT, LEAFONLY>(S, qo, qd, qm, qt, h, ctr);
             if (q == 0) {
                 if (!ok) break;
                 hit = true;
@@ -81,12 +84,12 @@ __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, 
     }
 }
 
-template <bool COUNT, int MINB>
+template <bool COUNT, int MINB, bool LEAFONLY>
 __global__ void __launch_bounds__(256, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     Ctr ctr;
     ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
     unsigned nHits = 0, nRefl = 0, nRefr = 0;
-    levelBody<COUNT>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
+    levelBody<COUNT, LEAFONLY>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
     flushCounters<COUNT>(A, ctr, nHits, nRefl, nRefr);
 }
 
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_frame(DevScene S, 
     if (stamper) stamps[0] = globalTimerNs();
     const int D = F.maxReflections;
     for (int level = 0; level <= D; level++) {
-        levelBody<COUNT>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
+        levelBody<COUNT, false>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
         grid.sync();
     }
     if (stamper) stamps[1] = globalTimerNs();
@@ -210,14 +213,17 @@ static inline int gridFor(long long n, int maxBlocks) {
 }
 
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
-                        long long upperBound, int maxBlocks, bool count, bool deep, cudaStream_t st) {
+                        long long upperBound, int maxBlocks, bool count, int kind, cudaStream_t st) {
     int grid = gridFor(upperBound, maxBlocks);
-    if (deep) {
-        if (count) k_level<true, XN_DEEP_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
-        else k_level<false, XN_DEEP_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
-    } else {
-        if (count) k_level<true, XN_LEVEL_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
-        else k_level<false, XN_LEVEL_MIN_BLOCKS><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    if (kind == 2) {          // deep octrees: high-occupancy build
+        if (count) k_level<true, XN_DEEP_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, XN_DEEP_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    } else if (kind == 1) {   // octrees with one split
+        if (count) k_level<true, XN_LEVEL_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, XN_LEVEL_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    } else {                  // every MeshOctree a single leaf: no expansion code, no stack
+        if (count) k_level<true, XN_LEAF_MIN_BLOCKS, true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, XN_LEAF_MIN_BLOCKS, true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
     }
     return cudaGetLastError();
 }

@@ -9,10 +9,10 @@
 namespace xn {
 
 // One wave of the trace loop: closest hit + shadow rays + shading for every ray of `level`.
-// upperBound only sizes the grid (the real count is read on the device).  deep selects the
-// high-occupancy (64-register) build of the per-thread kernel.
+// upperBound only sizes the grid (the real count is read on the device).  kind: 0 = every MeshOctree is a
+// single leaf (build without expansion code), 1 = shallow octrees, 2 = deep octrees (64-register build).
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
-                        long long upperBound, int maxBlocks, bool count, bool deep, cudaStream_t st);
+                        long long upperBound, int maxBlocks, bool count, int kind, cudaStream_t st);
 
 // The whole frame (all levels + resolve) in one cooperative launch; `blocks` must not exceed
 // frameKernelMaxBlocks().  stamps = 3 x uint64 device words (global timer at the phase boundaries).

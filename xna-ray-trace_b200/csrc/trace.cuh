@@ -375,16 +375,22 @@ __device__ __forceinline__ void walkLeafWarp(const DevScene& S, int src, const R
     }
 }
 
-// One thread, one ray: the whole walk.
-template <bool COUNT>
+// One thread, one ray: the whole walk.  LEAFONLY: every MeshOctree of the scene is a single leaf
+// (<= itemTreshold triangles per mesh, e.g. the Free_crate scene) — the expansion code and the stack
+// are compiled out, which is worth a third of the registers of the level kernel.
+template <bool COUNT, bool LEAFONLY>
 __device__ __forceinline__ bool traceMesh(const DevScene& S, const DevMesh* __restrict__ M, const RayPre& r, int ignoreTri,
                                           MeshHit& out, Ctr& ctr) {
-    WalkEntry stack[kMeshStack];
     Walk w;
     if (!walkStart<COUNT>(M, r, w, ctr)) return false;
-    for (;;) {
-        if (walkDescend<COUNT>(S, r, w, stack, ctr)) break;
-        walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+    if (LEAFONLY) {
+        while (w.have) walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+    } else {
+        WalkEntry stack[kMeshStack];
+        for (;;) {
+            if (walkDescend<COUNT>(S, r, w, stack, ctr)) break;
+            walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
+        }
     }
     out.tri = w.btri; out.key = w.bkey; out.u = w.bu; out.v = w.bv; out.d = w.bd;
     return w.btri >= 0;
@@ -398,7 +404,7 @@ struct Hit {
 };
 
 // Per-object block of OctreeSpatialManager.GetRayIntersection (OctreeSpatialManager.cs:347-428).
-template <bool COUNT>
+template <bool COUNT, bool LEAFONLY>
 __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
                                             float& minDistance, bool& found, Hit& best, Ctr& ctr) {
     const DevObj* __restrict__ O = &S.objs[objIdx];
@@ -418,7 +424,7 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
         if (!meshBoxSlab(M, r)) continue;
         MeshHit mh;
         int ign = (ignMesh == meshId) ? ignTri : -1;
-        const bool ok = traceMesh<COUNT>(S, M, r, ign, mh, ctr);
+        const bool ok = traceMesh<COUNT, LEAFONLY>(S, M, r, ign, mh, ctr);
         if (ok && mh.d < minDistance) {
             minDistance = mh.d;
             best.obj = objIdx; best.mesh = meshId; best.tri = mh.tri; best.key = mh.key;
@@ -432,7 +438,7 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
 // OctreeSpatialManager.GetRayIntersection.  Same group/early-exit semantics one level up; with
 // <= itemTreshold (20) objects the tree is the root leaf alone.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool LEAFONLY = false>
 __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
     if (!finite3(ro) || !finite3(rd)) return false;
     const bool cnt = COUNT;
@@ -464,7 +470,7 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
             for (int i = 0; i < w1; i++) {
                 const float before = ld;
                 const bool fb = lf;
-                objectQuery<COUNT>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
+                objectQuery<COUNT, LEAFONLY>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
                 if (lf && (!fb || ld < before)) lkey = w0 + i;
             }
             if (lf) {

@@ -89,7 +89,10 @@ struct XnartCtx {
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
     bool overlapLevels = true;  // XNART_OPT_OVERLAP_LEVELS: side stream for the shadow batches of the wavefront path
-    bool fuseFrame = true;   // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes
+    // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes.  Off by default: measured
+    // on B200 the grid-wide barriers cost more than the 17 launches they replace (0.63 vs 0.61 ms per 1080p
+    // crate frame), and a cooperative launch cannot share the GPU with NCCL's gather kernels.
+    bool fuseFrame = false;
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
     int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
@@ -616,7 +619,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         for (int L = 0; L <= D; L++) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
             if (!wave) {
-                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, deepScene(c), st));
+                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, deepScene(c) ? 2 : (c->maxMeshDepth >= 1 ? 1 : 0), st));
                 c->launches++;
                 continue;
             }

@@ -24,11 +24,29 @@ def gather_bands(part, height, world, band_rows_, rank, dst=0):
     """Assemble one frame from per-rank renders that filled only their own bands.
 
     `part` is a full-size (H, W) tensor whose foreign rows are don't-care.  Each rank contributes its
-    rows as one contiguous slab (equal sizes are not required); rank `dst` returns the full frame."""
-    rows = torch.tensor(band_rows(height, rank, world, band_rows_), device=part.device, dtype=torch.long)
-    mine = part.index_select(0, rows).contiguous()
+    rows as one contiguous slab (equal sizes are not required); rank `dst` returns the full frame.
+    When H is a multiple of the band height the bands of a rank are a strided view of the frame
+    (`frame.view(H/b, b, W)[rank::world]`): one copy out, one collective, one copy in per rank."""
     if world == 1:
         return part
+    if height % band_rows_ == 0:
+        nb = height // band_rows_
+        v = part.view(nb, band_rows_, *part.shape[1:])
+        mine = v[rank::world].contiguous()
+        counts = [len(range(r, nb, world)) for r in range(world)]
+        even = len(set(counts)) == 1
+        if rank == dst:
+            bufs = [torch.empty((counts[r],) + tuple(v.shape[1:]), dtype=part.dtype, device=part.device) for r in range(world)]
+            dist.gather(mine, bufs, dst=dst) if even else _gather_uneven(mine, bufs, rank, world, dst)
+            full = torch.empty_like(part)
+            fv = full.view(nb, band_rows_, *part.shape[1:])
+            for r in range(world):
+                fv[r::world] = bufs[r]
+            return full
+        dist.gather(mine, None, dst=dst) if even else _gather_uneven(mine, None, rank, world, dst)
+        return None
+    rows = torch.tensor(band_rows(height, rank, world, band_rows_), device=part.device, dtype=torch.long)
+    mine = part.index_select(0, rows).contiguous()
     counts = [len(band_rows(height, r, world, band_rows_)) for r in range(world)]
     if rank == dst:
         bufs = [torch.empty((counts[r],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device) for r in range(world)]
