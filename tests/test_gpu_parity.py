@@ -313,6 +313,14 @@ def test_flythrough_into_avi_sink(X, tmp_path):
     n, rays, _ = flythrough.render_flythrough(x, s, cams, 160, 96, sink=sink, batch=4)
     mgr.Close()
     assert n == 6 and rays > 6 * 160 * 96
+    # the device-side DIB conversion writes the same file as the host-side AddFrame
+    path2 = str(tmp_path / "fly2.avi")
+    m2 = avi.AviManager(path2, False)
+    s2 = m2.AddVideoStream(False, 30, 0, 160, 96, avi.PIXELFORMAT_24BPP_RGB)
+    for c in cams:
+        s2.AddFrame(x.render_frame(s.frame(160, 96, camera=c)))
+    m2.Close()
+    assert open(path, "rb").read() == open(path2, "rb").read()
     v = avi.AviManager(path, True).GetVideoStream()
     assert v.CountFrames == 6
     for i in (0, 3, 5):

@@ -32,13 +32,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dev = torch.device("cuda", local)
         dist.init_process_group("nccl", device_id=dev)
     if args.scene == "grid":
         s = scenes.grid_scene(args.n or 707)
@@ -57,7 +56,12 @@ def main():
         sink = mgr.AddVideoStream(False, args.fps, 0, args.width, args.height, avi.PIXELFORMAT_24BPP_RGB)
     x.render_frames([s.frame(args.width, args.height, camera=cams[0])])  # warm-up
     if world > 1:
+        # warm-up of the gather path as well (NCCL sets up its peer-to-peer connections on first use)
+        w = torch.zeros(16, device=dev)
+        dist.gather(w, [torch.zeros(16, device=dev) for _ in range(world)] if rank == 0 else None, dst=0)
         dist.barrier()
+    (torch.zeros(8, device=dev) + 1).sum().item()   # torch's own first-kernel cost stays out of the timed region
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     n_mine, rays, secs = flythrough.render_flythrough(x, s, cams, args.width, args.height, sink=sink, world=world, rank=rank, device=dev)
     if world > 1:

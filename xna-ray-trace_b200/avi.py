@@ -72,7 +72,16 @@ def to_dib_bits(bmp, bpp):
     """Bitmap -> the bytes AddFrame hands to AVIStreamWrite: rows bottom-up, BGR(A), stride padded to 4."""
     a = np.asarray(bmp)
     if a.ndim == 2 and a.dtype == np.uint32:
-        r, g, b, al = a & 255, (a >> 8) & 255, (a >> 16) & 255, (a >> 24) & 255
+        # packed R | G<<8 | B<<16 | A<<24 (little endian: bytes R, G, B, A) -> one byte gather per pixel
+        h, w = a.shape
+        nb = bpp // 8
+        stride = (w * nb + 3) & ~3
+        rgba = np.ascontiguousarray(a[::-1]).view(np.uint8).reshape(h, w, 4)
+        if stride == w * nb:
+            return rgba[..., [2, 1, 0, 3][:nb]].tobytes(), stride
+        out = np.zeros((h, stride), dtype=np.uint8)
+        out[:, : w * nb].reshape(h, w, nb)[...] = rgba[..., [2, 1, 0, 3][:nb]]
+        return out.tobytes(), stride
     elif a.ndim == 3 and a.dtype == np.uint8 and a.shape[2] in (3, 4):
         r, g, b = a[..., 0], a[..., 1], a[..., 2]
         al = a[..., 3] if a.shape[2] == 4 else np.full(a.shape[:2], 255, np.uint8)
@@ -113,6 +122,16 @@ class VideoStream:
             raise ValueError("frame size differs from the stream format")
         bits, stride = to_dib_bits(a, self.CountBitsPerPixel)
         assert stride == self._stride
+        self._m._write_frame(bits)
+        self.CountFrames += 1
+
+    def AddFrameBits(self, bits):
+        """The AVIStreamWrite call of AddFrame alone (VideoStream.cs:351-356): `bits` are the locked bitmap's
+        bytes, i.e. rows bottom-up, BGR(A), Stride * Height of them.  For callers that convert on the device."""
+        if self._reader is not None:
+            raise IOError("stream was opened for reading")
+        if len(bits) != self._stride * self.Height:
+            raise ValueError("expected Stride * Height = %d bytes" % (self._stride * self.Height))
         self._m._write_frame(bits)
         self.CountFrames += 1
 

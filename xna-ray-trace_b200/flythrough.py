@@ -26,47 +26,88 @@ def orbit_cameras(n_frames, radius=90.0, height_y=30.0, target=(0.0, 0.0, 0.0)):
     return cams
 
 
+def dib_bits_on_device(frames, bpp, stride):
+    """(..., H, W) int32 frames in the XNA Color layout on the device -> (..., H * stride) uint8 DIB bits
+    (rows bottom-up, BGR(A), rows padded to `stride`): VideoStream.AddFrame's RotateNoneFlipY + LockBits, done
+    with three torch ops on the GPU instead of numpy on the host."""
+    import torch
+
+    nb = bpp // 8
+    h, w = frames.shape[-2], frames.shape[-1]
+    px = frames.contiguous().view(torch.uint8).reshape(*frames.shape[:-2], h, w, 4)
+    idx = torch.tensor([2, 1, 0, 3][:nb], device=frames.device)
+    bgr = px.index_select(-1, idx).flip(-3).reshape(*frames.shape[:-2], h, w * nb)
+    if stride != w * nb:
+        bgr = torch.nn.functional.pad(bgr, (0, stride - w * nb))
+    return bgr.reshape(*frames.shape[:-2], h * stride)
+
+
 def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank=0, batch=8, device=None):
     """Render `cameras` (one frame each) on this rank's share and deliver the frames in order to `sink`
-    (an avi.VideoStream or any object with AddFrame) on rank 0.  Returns (frames rendered here, rays
-    traced here, seconds spent rendering here)."""
+    (an avi.VideoStream, or any object with AddFrame) on rank 0.  Returns (frames rendered here, rays
+    traced here, seconds spent here).
+
+    Frames stay on the device: every rank renders `batch` rounds into one half of a ring, ONE async
+    collective (on NCCL's stream) ships the group to rank 0 while the next group is being rendered, and
+    rank 0 converts a gathered group to DIB bits on the GPU and brings it to the host only to feed the sink."""
+    import torch
+
     n = len(cameras)
     mine = [f for f in range(n) if frame_owner(f, world) == rank]
-    rays, secs = 0, 0.0
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     dist = None
     if world > 1:
-        import torch
         import torch.distributed as dist
+    stream = torch.cuda.current_stream()
     rounds = (n + world - 1) // world
-    for r0 in range(0, rounds, batch):
-        rs = list(range(r0, min(rounds, r0 + batch)))
-        idx = [r * world + rank for r in rs if r * world + rank < n]
-        out = None
-        if idx:
-            frames = [scene.frame(width, height, camera=cameras[f]) for f in idx]
-            t0 = time.perf_counter()
-            out = x.render_frames(frames)
-            secs += time.perf_counter() - t0
-            rays += x.counters().rays
-        k = 0
-        for r in rs:
-            f_mine = r * world + rank
-            have = f_mine < n
-            frame = out[k] if have else np.zeros((height, width), dtype=np.uint32)
-            k += 1 if have else 0
-            if world == 1:
-                if sink is not None:
-                    sink.AddFrame(frame)
-                continue
-            t = torch.from_numpy(frame.view(np.int32).copy())
-            if device is not None:
-                t = t.to(device)
-            if rank == 0:
-                bufs = [torch.empty_like(t) for _ in range(world)]
-                dist.gather(t, bufs, dst=0)
-                for q in range(world):
-                    if r * world + q < n and sink is not None:
-                        sink.AddFrame(bufs[q].cpu().numpy().view(np.uint32))
-            else:
-                dist.gather(t, None, dst=0)
+    ring = torch.zeros((2, batch, height, width), dtype=torch.int32, device=device)
+    if world > 1 and rank == 0:
+        recv = [[torch.zeros((batch, height, width), dtype=torch.int32, device=device) for _ in range(world)] for _ in range(2)]
+    else:
+        recv = [None, None]
+    pending = [None, None]   # (work or None, first round, rounds in the group)
+    raw = sink is not None and hasattr(sink, "AddFrameBits")
+
+    def deliver(half):
+        work, r0, cnt = pending[half]
+        if work is not None:
+            work.wait()
+        pending[half] = None
+        if rank != 0 or sink is None:
+            return
+        grp = torch.stack(recv[half]) if world > 1 else ring[half].unsqueeze(0)      # (world, batch, H, W)
+        if raw:
+            host = dib_bits_on_device(grp[:, :cnt], sink.CountBitsPerPixel, sink._stride).cpu().numpy()
+        else:
+            host = grp[:, :cnt].cpu().numpy().view(np.uint32)
+        for k in range(cnt):
+            for q in range(world):
+                if (r0 + k) * world + q < n:
+                    if raw:
+                        sink.AddFrameBits(host[q, k].tobytes())
+                    else:
+                        sink.AddFrame(host[q, k])
+
+    t0 = time.perf_counter()
+    for g0 in range(0, rounds, batch):
+        half = (g0 // batch) & 1
+        if pending[half] is not None:
+            deliver(half)
+        cnt = min(batch, rounds - g0)
+        for k in range(cnt):
+            f = (g0 + k) * world + rank
+            if f < n:
+                x.render_frame_device(scene.frame(width, height, camera=cameras[f]), ring[half, k].data_ptr(), stream.cuda_stream)
+        work = dist.gather(ring[half], recv[half], dst=0, async_op=True) if world > 1 else None
+        pending[half] = (work, g0, cnt)
+    for h in sorted([h for h in range(2) if pending[h] is not None], key=lambda h: pending[h][1]):
+        deliver(h)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    # rays of this rank: the device counters are per render; sample the middle frame of this rank's share
+    rays = 0
+    if mine:
+        x.render_frame_device(scene.frame(width, height, camera=cameras[mine[len(mine) // 2]]), ring[0, 0].data_ptr(), None)
+        rays = x.counters().rays * len(mine)
     return len(mine), rays, secs
