@@ -326,3 +326,28 @@ def test_flythrough_into_avi_sink(X, tmp_path):
     for i in (0, 3, 5):
         assert np.array_equal(v.GetBitmap(i), x.render_frame(s.frame(160, 96, camera=cams[i])))
     x.close()
+
+
+def test_split_queries_give_the_same_frames(X, oracle_mod):
+    """Small batches are traced as 8 segment queries per ray (k_trace<.., SPLIT>): the first non-empty segment
+    reproduces the reference's first group of leaves.  Frames with splitting everywhere, nowhere and for the
+    deep levels only are identical (and equal to the oracle's)."""
+    for name, wh in (("grid", (320, 180)), ("soup", (200, 120))):
+        s = make_scene(name)
+        o = oracle_mod.Oracle()
+        scenes.upload(o, s)
+        x = X.Xnart()
+        x.set_option(records.OPT_TRAVERSAL, 2)
+        scenes.upload(x, s)
+        f = s.frame(*wh)
+        want = o.render_frame(f, n_threads=8)
+        for split in (1 << 24, 0, 20000):
+            x.set_option(records.OPT_SPLIT_RAYS, split)
+            assert np.array_equal(want, x.render_frame(f)), (name, split)
+        # axis-parallel directions take the slab test's containment branch inside split queries as well
+        f2 = s.frame(*wh, camera=scenes.CameraData((0.0, 60.0, 0.0), (0.0, 0.0, 1e-3)))
+        x.set_option(records.OPT_SPLIT_RAYS, 1 << 24)
+        a = x.render_frame(f2).copy()
+        x.set_option(records.OPT_SPLIT_RAYS, 0)
+        assert np.array_equal(a, x.render_frame(f2))
+        x.close()

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--frames", type=int, default=5)
     ap.add_argument("--check", action="store_true", help="compare a band of scanlines with the oracle")
     ap.add_argument("--count", action="store_true", help="run the instrumented kernels once and print work counters")
+    ap.add_argument("--split", type=int, default=None, help="XNART_OPT_SPLIT_RAYS")
     ap.add_argument("--traversal", type=int, default=0, help="XNART_OPT_TRAVERSAL: 0 auto, 1 thread per ray, 2 octet per ray")
     args = ap.parse_args()
 
@@ -47,6 +48,8 @@ def main():
     t_gen = time.time() - t0
     x = capi.Xnart()
     x.set_option(records.OPT_TRAVERSAL, args.traversal)
+    if args.split is not None:
+        x.set_option(records.OPT_SPLIT_RAYS, args.split)
     t0 = time.time()
     scenes.upload(x, s)
     t_up = time.time() - t0

@@ -65,7 +65,8 @@ struct DevMesh {
     int flags;           // bit0 useTexture, bit1 interpolateNormals, bit2 transparent
     int texOffset;       // first texel in texels[]
     int texW, texH;
-    int _pad[9];         // 128 bytes
+    float overshoot;     // max over internal nodes and axes of (consMax - own Max) >= 0 (split queries: node filter slack)
+    int _pad[8];         // 128 bytes
 };
 static_assert(sizeof(DevMesh) == 128, "DevMesh layout");
 enum { MESH_USE_TEXTURE = 1, MESH_INTERP_NORMALS = 2, MESH_TRANSPARENT = 4 };
@@ -117,7 +118,13 @@ struct TraceJob {
     const unsigned int* segCount;
     unsigned int* fetch;     // work counter, zero at launch
     unsigned int nSeg, segStride;
+    // Split queries: batches of at most splitMax rays are traced as kSplit segment queries per ray
+    // (k_trace<.., true>; results in outSplit[(ray * kSplit + segment) * 2 ..]); larger batches by
+    // k_trace<.., false>.  Both kernels are launched, the one that does not apply exits at once.
+    int4* outSplit;
+    unsigned int splitMax;   // 0: never split
 };
+constexpr int kSplit = 8;
 
 struct DevFrame {
     float inv[16];       // Invert(Identity * view * proj), computed once per frame on the host
@@ -157,6 +164,9 @@ struct DevArena {
     float4* shD[2];
     int2* shIgn[2];
     int4* shHit[2];      // 2 per shadow slot
+    int4* hitSplit[2];   // split batches: kSplit records per ray of the level (<= splitMax rays)
+    int4* shSplit[2];    // ... per shadow ray
+    unsigned int splitMax;
     unsigned int* shadowHits;   // [maxLevels+2] hits per level (= rays per shadow segment)
     unsigned int* fetch;        // [2*(maxLevels+2)] work counters of the trace launches
 };

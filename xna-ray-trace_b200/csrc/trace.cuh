@@ -85,13 +85,18 @@ __device__ __forceinline__ bool slabAxis(float mn, float mx, float p, float inv,
 
 // BoundingBox.Intersects(ref Ray, out float?) — XNA 4.0 form.  tmin only grows and tmax only
 // shrinks, so the framework's per-axis `if (tmin > tmax) return null` equals one test at the end.
-__device__ __forceinline__ bool slab(float3 mn, float3 mx, const RayPre& r, float& t) {
+__device__ __forceinline__ bool slab2(float3 mn, float3 mx, const RayPre& r, float& t, float& tExit) {
     float tmin = 0.0f, tmax = FLT_MAX;
     bool ok = slabAxis(mn.x, mx.x, r.o.x, r.inv.x, r.par & 1, tmin, tmax);
     ok = slabAxis(mn.y, mx.y, r.o.y, r.inv.y, r.par & 2, tmin, tmax) && ok;
     ok = slabAxis(mn.z, mx.z, r.o.z, r.inv.z, r.par & 4, tmin, tmax) && ok;
     t = tmin;
+    tExit = tmax;
     return ok && !(tmin > tmax);
+}
+__device__ __forceinline__ bool slab(float3 mn, float3 mx, const RayPre& r, float& t) {
+    float tExit;
+    return slab2(mn, mx, r, t, tExit);
 }
 
 // Vector3.Transform with the matrix fetched as four 16-byte rows (SceneObject.World / InverseWorld
@@ -182,14 +187,29 @@ __device__ __forceinline__ void fullTriangleTest(const float4 nt, const float4 v
 // Visiting order, K rule, prune rule and tie-break are those of the oracle's pruned walk, so the
 // work counters agree with it exactly.
 // ---------------------------------------------------------------------------------------------
+// Ray segment of a split query (wavefront.cu, k_trace<.., SPLIT>): only leaves whose entry distance t
+// satisfies a <= t < b belong to the segment.  The reference answers a query from the group of leaves
+// with the SMALLEST entry distance that holds an accepted triangle (MeshOctree.cs:281-306), and leaves
+// with bit-equal t fall into the same segment, so the answer of the first non-empty segment IS the
+// reference's answer; the segments of a ray can therefore be walked by different lanes at the same
+// time.  Internal nodes are skipped when no descendant leaf can lie in the segment: descendant entry
+// distances lie in [entry, exit] of the node's conservative box, which differs from the node's own
+// box by at most `overshoot` (DevMesh) in plane position, i.e. by overshoot * max|1/d| in t; the
+// slack below is several times that plus a relative term for the rounding of t itself.
+struct Seg {
+    float a, b;       // leaf filter: a <= t < b
+    float aLo, bHi;   // node filter: skip when exit < aLo or entry >= bHi
+};
+
 template <bool COUNT>
-__device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const RayPre& r, Walk& w, Ctr& ctr) {
-    float t0;
+__device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const RayPre& r, Walk& w, Ctr& ctr, float* tExitOut = nullptr) {
+    float t0, t1;
     if (COUNT) ctr.nBox++;
     // rootBox[0..5], rootA, rootB = bytes 24..55 of DevMesh
     const float2 rb0 = __ldg(reinterpret_cast<const float2*>(M->rootBox));
     const float4 rb1 = __ldg(reinterpret_cast<const float4*>(M->rootBox + 2));
-    if (!slab(make_float3(rb0.x, rb0.y, rb1.x), make_float3(rb1.y, rb1.z, rb1.w), r, t0)) return false;
+    if (!slab2(make_float3(rb0.x, rb0.y, rb1.x), make_float3(rb1.y, rb1.z, rb1.w), r, t0, t1)) return false;
+    if (tExitOut) *tExitOut = t1;
     const int2 rd = __ldg(reinterpret_cast<const int2*>(&M->rootA));
     w.K = INFINITY; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
     w.ca = rd.x; w.cb = rd.y; w.ct = t0; w.have = true; w.sp = 0;
@@ -197,8 +217,9 @@ __device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const R
 }
 
 // Returns true when the walk is over (nothing held, stack empty).
-template <bool COUNT, int STEPS = XN_DESCEND_MAX>
-__device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, Walk& w, WalkEntry* __restrict__ stack, Ctr& ctr) {
+template <bool COUNT, int STEPS = XN_DESCEND_MAX, bool SEG = false>
+__device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, Walk& w, WalkEntry* __restrict__ stack, Ctr& ctr,
+                                            const Seg& seg = Seg()) {
     const bool ox = (r.oct & 4) != 0, oy = (r.oct & 2) != 0, oz = (r.oct & 1) != 0;
 #pragma unroll 1
     for (int step = 0; step < STEPS; step++) {
@@ -265,7 +286,9 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
                 const int2 d = ds[p];
                 // empty leaves are dropped; a leaf entered after K can never matter; internal nodes are
                 // re-examined when popped (conservative box)
-                if (!(tmin > tmax) && d.y != 0 && (d.y < 0 || !(tmin > w.K))) {
+                bool take = !(tmin > tmax) && d.y != 0 && (d.y < 0 || !(tmin > w.K));
+                if (SEG) take = take && (d.y < 0 ? !(tmax < seg.aLo || tmin >= seg.bHi) : (tmin >= seg.a && tmin < seg.b));
+                if (take) {
                     if (w.have) { stack[w.sp] = make_int4(w.ca, w.cb, __float_as_int(w.ct), 0); w.sp++; }
                     w.ca = d.x; w.cb = d.y; w.ct = tmin; w.have = true;
                 }
@@ -282,7 +305,10 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
                 const bool h = slab(make_float3(i ? lx[1] : lx[0], j ? ly[1] : ly[0], k ? lz[1] : lz[0]),
                                     make_float3(i ? hx[1] : hx[0], j ? hy[1] : hy[0], k ? hz[1] : hz[0]), r, tc);
                 const int2 d = ds[p];
-                if (h && d.y != 0 && (d.y < 0 || !(tc > w.K))) {
+                // (segments: the containment branch has no exit distance at hand; internal nodes are kept)
+                bool take = h && d.y != 0 && (d.y < 0 || !(tc > w.K));
+                if (SEG) take = take && (d.y < 0 ? !(tc >= seg.bHi) : (tc >= seg.a && tc < seg.b));
+                if (take) {
                     if (w.have) { stack[w.sp] = make_int4(w.ca, w.cb, __float_as_int(w.ct), 0); w.sp++; }
                     w.ca = d.x; w.cb = d.y; w.ct = tc; w.have = true;
                 }

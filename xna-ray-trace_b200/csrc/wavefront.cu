@@ -62,12 +62,25 @@ __global__ void __launch_bounds__(256) k_gen_primary(DevFrame F, DevArena A) {
 // ---------------------------------------------------------------------------------------------
 // persistent trace kernel
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
+// SPLIT: every ray of a SMALL batch is traced as kSplit segment queries (trace.cuh: Seg), each by its own
+// lane.  Deep recursion levels hold few rays, and a few of them graze the surface through hundreds of
+// leaves: one lane walking such a ray alone kept the GPU waiting for most of the launch (ncu launch
+// list, profiles/r01h: 42 M warp instructions in 0.68 ms).  Cutting the ray into segments by entry
+// distance divides that serial walk by up to kSplit and gives the same answer (the first non-empty
+// segment's).  The instrumented build never splits: its counters are those of the canonical walk.
+template <bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, TraceJob J, unsigned long long* __restrict__ counters) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned segCount = *J.segCount;
-    const unsigned total = segCount * J.nSeg;
+    const unsigned nRays = segCount * J.nSeg;
+    const bool splitBatch = !COUNT && J.splitMax != 0u && nRays <= J.splitMax && S.nPairs == 1;
+    if (splitBatch != SPLIT) return;
+    const unsigned total = SPLIT ? nRays * (unsigned)kSplit : nRays;
+    Seg seg;
+    seg.a = seg.aLo = -INFINITY; seg.b = seg.bHi = INFINITY;
+    int mySeg = 0;
+    size_t outIdx = 0;
     WalkEntry stack[kMeshStack];
     Ctr ctr;
     ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
@@ -102,9 +115,12 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
             if (slot < 0) {
                 const unsigned i = base + (unsigned)__popc(idleMask & ((1u << lane) - 1u));
                 if (i < total) {
-                    unsigned q = 0, h = i;
-                    if (J.nSeg > 1) { q = i / segCount; h = i - q * segCount; }
+                    unsigned iray = i;
+                    if (SPLIT) { iray = i / (unsigned)kSplit; mySeg = (int)(i - iray * (unsigned)kSplit); }
+                    unsigned q = 0, h = iray;
+                    if (J.nSeg > 1) { q = iray / segCount; h = iray - q * segCount; }
                     slot = (int)(q * J.segStride + h);
+                    outIdx = SPLIT ? (size_t)i : (size_t)slot;
                     pi = 0; walking = false;
                     bestD = FLT_MAX;
                     // a non-finite ray fails every triangle test; the scene root must be hit
@@ -145,15 +161,30 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
                     if (COUNT) ctr.nBox++;
                     if (!meshBoxSlab(M, r)) { pi++; continue; }
                     ignoreTri = (ig.x == pr.y) ? ig.y : -1;
-                    if (!walkStart<COUNT>(M, r, w, ctr)) { pi++; continue; }
+                    float tExit = 0.0f;
+                    if (!walkStart<COUNT>(M, r, w, ctr, &tExit)) { pi++; continue; }
+                    if (SPLIT) {
+                        // segment mySeg of [root entry, root exit]; the first reaches back to -inf, the last to +inf
+                        const float len = tExit - w.ct;
+                        const float lo = w.ct + len * ((float)mySeg * (1.0f / kSplit));
+                        const float hi = w.ct + len * ((float)(mySeg + 1) * (1.0f / kSplit));
+                        seg.a = (mySeg == 0) ? -INFINITY : lo;
+                        seg.b = (mySeg == kSplit - 1) ? INFINITY : hi;
+                        const float maxInv = fmaxf((r.par & 1) ? 0.0f : fabsf(r.inv.x), fmaxf((r.par & 2) ? 0.0f : fabsf(r.inv.y), (r.par & 4) ? 0.0f : fabsf(r.inv.z)));
+                        const float slack = 8.0f * __ldg(&M->overshoot) * maxInv + 1e-5f * (fabsf(w.ct) + fabsf(tExit)) + 1e-30f;
+                        seg.aLo = seg.a - slack; seg.bHi = seg.b + slack;
+                        // a root that is itself a leaf belongs to the segment that contains its entry distance
+                        if (w.cb >= 0 && !(w.ct >= seg.a && w.ct < seg.b)) { pi++; continue; }
+                    }
                     walking = true;
                 } while (!walking && pi < S.nPairs);
             }
             if (!walking) {
                 // every pair tried: the ray is finished (a hit was written when it became the best)
                 if (bestD == FLT_MAX) {
-                    J.out[2 * (size_t)slot] = make_int4(-1, -1, -1, 0);
-                    J.out[2 * (size_t)slot + 1] = make_int4(0, 0, 0, 0);
+                    int4* __restrict__ o = SPLIT ? J.outSplit : J.out;
+                    o[2 * outIdx] = make_int4(-1, -1, -1, 0);
+                    o[2 * outIdx + 1] = make_int4(0, 0, 0, 0);
                 }
                 slot = -1;
             }
@@ -180,7 +211,7 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
                 walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
             }
         } else {
-            if (walking && !wantLeaf) over = walkDescend<COUNT, XN_TRACE_DESCEND>(S, r, w, stack, ctr);
+            if (walking && !wantLeaf) over = walkDescend<COUNT, XN_TRACE_DESCEND, SPLIT>(S, r, w, stack, ctr, seg);
         }
         __syncwarp();
         if (walking && over) {
@@ -189,8 +220,9 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
             if (w.btri >= 0 && w.bd < bestD) {
                 bestD = w.bd;
                 const int2 pr = __ldg(&S.pairs[pi]);
-                J.out[2 * (size_t)slot] = make_int4(pr.x, pr.y, w.btri, w.bkey);
-                J.out[2 * (size_t)slot + 1] = make_int4(__float_as_int(w.bu), __float_as_int(w.bv), __float_as_int(w.bd), 1);
+                int4* __restrict__ o = SPLIT ? J.outSplit : J.out;
+                o[2 * outIdx] = make_int4(pr.x, pr.y, w.btri, w.bkey);
+                o[2 * outIdx + 1] = make_int4(__float_as_int(w.bu), __float_as_int(w.bv), __float_as_int(w.bd), 1);
             }
             pi++;
             walking = false;
@@ -219,6 +251,23 @@ __device__ __forceinline__ Hit hitOf(const DevScene& S, const int4 a, const int4
     return h;
 }
 
+// Result of ray `iray` of a batch of `nRays`: the record itself, or — when the batch was traced as split
+// queries — the record of its first segment that found anything.
+__device__ __forceinline__ void fetchHit(const int4* __restrict__ plain, const int4* __restrict__ split, bool splitBatch, size_t plainIdx,
+                                         size_t iray, int4& a, int4& b) {
+    if (!splitBatch) { a = plain[2 * plainIdx]; b = plain[2 * plainIdx + 1]; return; }
+    const int4* __restrict__ p = split + 2 * iray * kSplit;
+    a = make_int4(-1, -1, -1, 0); b = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int sgm = 0; sgm < kSplit; sgm++) {
+        const int4 x = p[2 * sgm];
+        if (x.x >= 0) { a = x; b = p[2 * sgm + 1]; return; }
+    }
+}
+__device__ __forceinline__ bool isSplitBatch(const DevScene& S, const DevArena& A, unsigned nRays) {
+    return A.splitMax != 0u && nRays <= A.splitMax && S.nPairs == 1;
+}
+
 __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     const unsigned count = A.levelCount[level];
     const unsigned base = A.levelBase[level];
@@ -226,11 +275,12 @@ __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevAren
     if (blockIdx.x == 0 && threadIdx.x == 0) A.levelBase[level + 1] = nextBase;
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
     const int par = level & 1;
-    const int4* __restrict__ hit = A.hit[par];
+    const bool splitL = isSplitBatch(S, A, count);
     unsigned nHits = 0, nRefl = 0, nRefr = 0;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
-        const int4 ha = hit[2 * (size_t)idx], hb = hit[2 * (size_t)idx + 1];
+        int4 ha, hb;
+        fetchHit(A.hit[par], A.hitSplit[par], splitL, idx, idx, ha, hb);
         if (ha.x < 0) {
             A.color[node] = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);  // RayTracer.cs:732
             A.flags[node] = 0u;
@@ -287,11 +337,13 @@ __global__ void __launch_bounds__(256) k_shade_b(DevScene S, DevFrame F, DevAren
     const unsigned base = A.levelBase[level];
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
     const int par = level & 1;
-    const int4* __restrict__ hit = A.hit[par];
-    const int4* __restrict__ shHit = A.shHit[par];
+    const bool splitL = isSplitBatch(S, A, count);
+    const unsigned nShadowHits = A.shadowHits[level];
+    const bool splitS = isSplitBatch(S, A, nShadowHits * (unsigned)F.nLights);
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
-        const int4 ha = hit[2 * (size_t)idx], hb = hit[2 * (size_t)idx + 1];
+        int4 ha, hb;
+        fetchHit(A.hit[par], A.hitSplit[par], splitL, idx, idx, ha, hb);
         if (ha.x < 0) continue;
         Hit h = hitOf(S, ha, hb);
         const float4 pa = A.nodeA[node], nb = A.nodeB[node];
@@ -301,7 +353,8 @@ __global__ void __launch_bounds__(256) k_shade_b(DevScene S, DevFrame F, DevAren
         V3 lightResult = mk(0.0f, 0.0f, 0.0f);
         for (int q = 0; q < F.nLights; q++) {
             const size_t s = (size_t)q * A.rayCapacity + k;
-            const int4 sa = shHit[2 * s], sb = shHit[2 * s + 1];
+            int4 sa, sb;
+            fetchHit(A.shHit[par], A.shSplit[par], splitS, s, (size_t)q * nShadowHits + k, sa, sb);
             const Hit sh = hitOf(S, sa, sb);
             lightResult = addLight(S, lights[q], sa.x >= 0, sh, A.shO[par][s].w, h.pos, N, lightResult);
         }
@@ -369,8 +422,8 @@ static inline int gridFor(long long n, int maxBlocks) {
 
 int traceKernelBlocksPerSm(bool count) {
     int perSm = 0;
-    cudaError_t e = count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true>, 256, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false>, 256, 0);
+    cudaError_t e = count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true, false>, 256, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false, false>, 256, 0);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return perSm;
 }
@@ -381,8 +434,13 @@ cudaError_t launchGenPrimary(const DevFrame& F, const DevArena& A, int maxBlocks
 }
 
 cudaError_t launchTrace(const DevScene& S, const TraceJob& J, unsigned long long* counters, int blocks, bool count, cudaStream_t st) {
-    if (count) k_trace<true><<<blocks, 256, 0, st>>>(S, J, counters);
-    else k_trace<false><<<blocks, 256, 0, st>>>(S, J, counters);
+    if (count) {
+        k_trace<true, false><<<blocks, 256, 0, st>>>(S, J, counters);
+    } else {
+        k_trace<false, false><<<blocks, 256, 0, st>>>(S, J, counters);
+        // the split build handles the batch instead when it is small (decided on the device, see k_trace)
+        if (J.splitMax != 0u && S.nPairs == 1) k_trace<false, true><<<blocks, 256, 0, st>>>(S, J, counters);
+    }
     return cudaGetLastError();
 }
 

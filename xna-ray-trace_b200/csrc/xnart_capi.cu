@@ -88,6 +88,7 @@ struct XnartCtx {
     bool countKernels = false;
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
+    int64_t splitRays = 131072;  // XNART_OPT_SPLIT_RAYS: batches up to this many rays are traced as segment queries (0 = never)
     bool overlapLevels = true;  // XNART_OPT_OVERLAP_LEVELS: side stream for the shadow batches of the wavefront path
     // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes.  Off by default: measured
     // on B200 the grid-wide barriers cost more than the 17 launches they replace (0.63 vs 0.61 ms per 1080p
@@ -221,6 +222,9 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
             c->traceSemantics = (int)value; return XNART_OK;
         case XNART_OPT_FUSE_FRAME: c->fuseFrame = value != 0; return XNART_OK;
         case XNART_OPT_OVERLAP_LEVELS: c->overlapLevels = value != 0; return XNART_OK;
+        case XNART_OPT_SPLIT_RAYS:
+            if (value < 0 || value > (1 << 24)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "split threshold out of range");
+            c->splitRays = value; return XNART_OK;
         case XNART_OPT_TRAVERSAL:
             if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
             c->traversalMode = (int)value; return XNART_OK;
@@ -353,6 +357,15 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         std::memcpy(dm.box, m.box.mn, 12);
         std::memcpy(dm.box + 3, m.box.mx, 12);
         dm.rootNode = (int)nodeBase;
+        {
+            float ov = 0.0f;
+            for (size_t n = 0; n < m.tree.nodeCount(); n++) {
+                if (m.tree.w1[n] >= 0) continue;
+                const size_t k = (size_t)(-1 - m.tree.w1[n]);
+                for (int a = 0; a < 3; a++) ov = std::max(ov, m.tree.consMax[3 * k + a] - m.tree.hi[3 * n + a]);
+            }
+            dm.overshoot = ov;
+        }
         std::memcpy(dm.rootBox, &m.tree.lo[0], 12);
         std::memcpy(dm.rootBox + 3, &m.tree.hi[0], 12);
         if (m.tree.w1[0] >= 0) { dm.rootA = m.tree.w0[0] + (int)refBase; dm.rootB = m.tree.w1[0]; }
@@ -475,10 +488,12 @@ static int localRowsOf(int H, int shardIndex, int shardCount, int bandRows) {
 
 static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned rays, bool wave = false, int nLights = 0) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const unsigned splitMax = (wave && c->splitRays > 0 && c->nPairs == 1 && !c->countKernels) ? (unsigned)c->splitRays : 0u;
+    const size_t splitBytes = al((size_t)splitMax * kSplit * 32);
     const size_t shRays = wave ? (size_t)rays * (size_t)std::max(nLights, 1) : 0;
     size_t need = al((size_t)nodes * 16) * 2 + al((size_t)nodes * 8) + al((size_t)nodes * 4) * 2 +
                   2 * (al((size_t)rays * 16) * 2 + al((size_t)rays * 8));
-    if (wave) need += 2 * (al((size_t)rays * 32) + al(shRays * 16) * 2 + al(shRays * 8) + al(shRays * 32));
+    if (wave) need += 2 * (al((size_t)rays * 32) + al(shRays * 16) * 2 + al(shRays * 8) + al(shRays * 32)) + 4 * splitBytes;
     if (need > d.arenaBytes) {
         CU_TRY(c, cudaStreamSynchronize(d.stream));
         cudaFree(d.arenaBlock);
@@ -508,7 +523,10 @@ static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned ray
             A.shIgn[q] = (int2*)take(shRays * 8);
             A.shHit[q] = (int4*)take(shRays * 32);
         }
+        A.hitSplit[q] = (wave && splitMax) ? (int4*)take((size_t)splitMax * kSplit * 32) : nullptr;
+        A.shSplit[q] = (wave && splitMax) ? (int4*)take((size_t)splitMax * kSplit * 32) : nullptr;
     }
+    A.splitMax = splitMax;
     A.levelCount = d.levelWords;
     A.levelBase = d.levelWords + (kMaxLevels + 2);
     A.overflow = d.levelWords + 2 * (kMaxLevels + 2);
@@ -619,7 +637,10 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         for (int L = 0; L <= D; L++) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
             if (!wave) {
-                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, maxBlocks, c->countKernels, deepScene(c) ? 2 : (c->maxMeshDepth >= 1 ? 1 : 0), st));
+                // deep levels usually hold a small fraction of the rays: a grid of resident blocks only (the
+                // kernels are grid-stride loops) keeps the cost of a nearly empty launch down
+                const int cap = (L >= 2 && !c->hasTransparent) ? d.smCount * 3 : maxBlocks;
+                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, cap, c->countKernels, deepScene(c) ? 2 : (c->maxMeshDepth >= 1 ? 1 : 0), st));
                 c->launches++;
                 continue;
             }
@@ -634,6 +655,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
             TraceJob J;
             J.rayO = A.rayO[in]; J.rayD = A.rayD[in]; J.rayIgn = A.rayIgn[in]; J.out = A.hit[in];
             J.segCount = &A.levelCount[L]; J.fetch = &A.fetch[2 * L]; J.nSeg = 1; J.segStride = 0;
+            J.outSplit = A.hitSplit[in]; J.splitMax = A.splitMax;
             CU_TRY(c, launchTrace(d.scene, J, d.counters, tb, c->countKernels, st));
             CU_TRY(c, launchShadeA(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, st));
             c->launches += 2;
@@ -644,6 +666,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
                 TraceJob Sj;
                 Sj.rayO = A.shO[in]; Sj.rayD = A.shD[in]; Sj.rayIgn = A.shIgn[in]; Sj.out = A.shHit[in];
                 Sj.segCount = &A.shadowHits[L]; Sj.fetch = &A.fetch[2 * L + 1]; Sj.nSeg = (unsigned)F.nLights; Sj.segStride = A.rayCapacity;
+                Sj.outSplit = A.shSplit[in]; Sj.splitMax = A.splitMax;
                 CU_TRY(c, launchTrace(d.scene, Sj, d.counters, tb, c->countKernels, ss));
                 c->launches++;
             }
@@ -659,7 +682,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         if (p0 == 0) CU_TRY(c, cudaEventRecord(d.ev[1], st));
         for (int L = D - 1; L >= 0; L--) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
-            CU_TRY(c, launchResolve(F, d.arena, L, (long long)ub, maxBlocks, devOut, st));
+            CU_TRY(c, launchResolve(F, d.arena, L, (long long)ub, (L >= 2 && !c->hasTransparent) ? d.smCount * 2 : maxBlocks, devOut, st));
             c->launches++;
         }
         if (D == 0) {
@@ -951,6 +974,7 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
         TR_TRY(launchPackRays(dr, di, n, qo, qd, qi, d.smCount * 8, d.stream));
         TraceJob J;
         J.rayO = qo; J.rayD = qd; J.rayIgn = qi; J.out = qh; J.segCount = qw; J.fetch = qw + 1; J.nSeg = 1; J.segStride = 0;
+        J.outSplit = nullptr; J.splitMax = 0;
         TR_TRY(launchTrace(d.scene, J, d.counters, c->countKernels ? d.traceBlocksCount : d.traceBlocks, c->countKernels, d.stream));
         TR_TRY(launchUnpackHits(d.scene, qh, n, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, d.stream));
         c->launches += 3;
