@@ -116,6 +116,7 @@ enum {
     XNART_OPT_TRAVERSAL = 4,     /* kernel schedule: 0 auto, 1 one thread per ray, 2 wavefront (persistent trace kernel) */
     XNART_OPT_FUSE_FRAME = 5,    /* 0/1 (default 0): shallow scenes render a frame in one cooperative launch */
     XNART_OPT_OVERLAP_LEVELS = 6, /* 0/1 (default 1): wavefront path runs a level's shadow batch beside the next level */
+    XNART_OPT_CHAIN_RESOLVE = 8, /* 0/1 (default 1): opaque scenes fold a pixel's reflection chain in one launch */
     XNART_OPT_SPLIT_RAYS = 7     /* wavefront path: batches of at most this many rays are traced as 8 segment queries per
                                     ray, which shortens the serial tail of deep levels (default 131072, 0 = never) */
 };

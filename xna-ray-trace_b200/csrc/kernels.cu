@@ -165,6 +165,35 @@ __global__ void __launch_bounds__(256) k_resolve(DevFrame F, DevArena A, int lev
     resolveBody(F, A, level, out);
 }
 
+// Opaque scenes: the path of a pixel is a chain (one reflection ray per hit, RayTracer.cs:545-559), so one
+// thread can fold it without the per-level launches: walk down to the node whose colour is final (a miss, or
+// the deepest level), then apply CastRay's combination (:584, :705) level by level on the way back up, packing
+// to the 8-bit Color at every level exactly as the recursion does.  Same arithmetic as resolveBody.
+__global__ void __launch_bounds__(256) k_resolve_chain(DevFrame F, DevArena A, uint32_t* __restrict__ out) {
+    const unsigned count = (unsigned)F.chunkPixels;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        unsigned path[32];   // kMaxLevels + 2 in xnart_capi.cu
+        int depth = 0;
+        unsigned node = idx;
+        while (A.flags[node] && depth < 31) {
+            path[depth++] = node;
+            const unsigned child = A.nodeC[node].x;
+            if (!(child < A.nodeCapacity)) { node = 0xFFFFFFFFu; break; }
+            node = child;
+        }
+        uint32_t col = (node != 0xFFFFFFFFu) ? A.color[node] : 0xFF000000u;
+        for (int k = depth - 1; k >= 0; k--) {
+            const float4 a = A.nodeA[path[k]], b = A.nodeB[path[k]];
+            // Lerp(reflectionColor.ToVector3(), surfaceColor, 1 - Reflectiveness) * lightResult (:584)
+            const V3 cv = mulv(lerp(unpackColor(col), mk(b.x, b.y, b.z), a.w), mk(a.x, a.y, a.z));
+            col = packColor(cv, F.semantics);  // :705
+        }
+        int x, y;
+        pixelOf(F, F.pixelBase + idx, x, y);
+        out[(size_t)y * (size_t)F.vpW + (size_t)x] = col;  // renderTargetData[y*W + x] (:425)
+    }
+}
+
 // Batch form of ISpatialManager.GetRayIntersection for parity tests (one thread per ray).
 template <bool COUNT>
 __global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_trace_rays(DevScene S, const float* __restrict__ rays6, long long n,
@@ -244,6 +273,11 @@ cudaError_t launchFrame(const DevScene& S, const DevFrame& F, const DevArena& A,
     void* args[] = {(void*)&S, (void*)&F, (void*)&A, (void*)&lights, (void*)&out, (void*)&stamps};
     const void* fn = count ? (const void*)k_frame<true> : (const void*)k_frame<false>;
     return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, st);
+}
+
+cudaError_t launchResolveChain(const DevFrame& F, const DevArena& A, int maxBlocks, uint32_t* out, cudaStream_t st) {
+    k_resolve_chain<<<gridFor(F.chunkPixels, maxBlocks), 256, 0, st>>>(F, A, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long long upperBound, int maxBlocks,

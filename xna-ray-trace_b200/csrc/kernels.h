@@ -24,6 +24,9 @@ cudaError_t launchFrame(const DevScene& S, const DevFrame& F, const DevArena& A,
 cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long long upperBound, int maxBlocks,
                           uint32_t* out, cudaStream_t st);
 
+// Opaque scenes (every path a chain): the whole bottom-up resolve in one launch, one thread per pixel.
+cudaError_t launchResolveChain(const DevFrame& F, const DevArena& A, int maxBlocks, uint32_t* out, cudaStream_t st);
+
 // Batch closest-hit queries (xnart_trace_rays).
 cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,

@@ -88,6 +88,7 @@ struct XnartCtx {
     bool countKernels = false;
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
+    bool chainResolve = true;   // XNART_OPT_CHAIN_RESOLVE: opaque scenes resolve a pixel's chain in one launch
     int64_t splitRays = 131072;  // XNART_OPT_SPLIT_RAYS: batches up to this many rays are traced as segment queries (0 = never)
     bool overlapLevels = true;  // XNART_OPT_OVERLAP_LEVELS: side stream for the shadow batches of the wavefront path
     // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes.  Off by default: measured
@@ -222,6 +223,7 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
             c->traceSemantics = (int)value; return XNART_OK;
         case XNART_OPT_FUSE_FRAME: c->fuseFrame = value != 0; return XNART_OK;
         case XNART_OPT_OVERLAP_LEVELS: c->overlapLevels = value != 0; return XNART_OK;
+        case XNART_OPT_CHAIN_RESOLVE: c->chainResolve = value != 0; return XNART_OK;
         case XNART_OPT_SPLIT_RAYS:
             if (value < 0 || value > (1 << 24)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "split threshold out of range");
             c->splitRays = value; return XNART_OK;
@@ -680,6 +682,11 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
             }
         }
         if (p0 == 0) CU_TRY(c, cudaEventRecord(d.ev[1], st));
+        if (!c->hasTransparent && c->chainResolve) {
+            CU_TRY(c, launchResolveChain(F, d.arena, maxBlocks, devOut, st));
+            c->launches++;
+            continue;
+        }
         for (int L = D - 1; L >= 0; L--) {
             double ub = c->hasTransparent ? std::min((double)rayCap, (double)F.chunkPixels * std::ldexp(1.0, L)) : (double)F.chunkPixels;
             CU_TRY(c, launchResolve(F, d.arena, L, (long long)ub, (L >= 2 && !c->hasTransparent) ? d.smCount * 2 : maxBlocks, devOut, st));
