@@ -75,7 +75,8 @@ struct DevObj {
     float world[16];     // SceneObject.World (row-major; column 4 unused by Vector3.Transform)
     float inv[16];       // SceneObject.InverseWorld
     int meshStart, meshCount;  // range in objMeshIds[]
-    int _pad[2];
+    int xformClass;            // index of the first object whose InverseWorld has the same bits
+    int _pad;
 };
 
 struct DevLight {

@@ -430,19 +430,27 @@ struct Hit {
 };
 
 // Per-object block of OctreeSpatialManager.GetRayIntersection (OctreeSpatialManager.cs:347-428).
+// The object-space ray depends on the object through InverseWorld only, so objects whose matrices are
+// bit-identical (DevObj.xformClass: e.g. every object placed with the identity) share it: `cls`/`r`/`rOk`
+// carry the ray of the class seen last from one call to the next.
 template <bool COUNT, bool LEAFONLY>
 __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
-                                            float& minDistance, bool& found, Hit& best, Ctr& ctr) {
+                                            float& minDistance, bool& found, Hit& best, Ctr& ctr, int& cls, RayPre& r, bool& rOk) {
     const DevObj* __restrict__ O = &S.objs[objIdx];
-    // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (:358-364)
-    V3 rdp = add(ro, rd);
-    const M43 Wi = loadM43(O->inv);
-    V3 v1 = transform43(ro, Wi);
-    V3 v2 = transform43(rdp, Wi);
-    V3 dd = normalize(sub(v2, v1));
-    if (!finite3(v1) || !finite3(dd)) return;  // a non-finite ray fails every triangle test (NaN comparisons)
-    RayPre r = prepRay(v1, dd);
-    const int ms = O->meshStart, mc = O->meshCount;
+    const int4 om = __ldg(reinterpret_cast<const int4*>(&O->meshStart));  // meshStart, meshCount, xformClass, -
+    if (om.z != cls) {
+        cls = om.z;
+        // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (:358-364)
+        V3 rdp = add(ro, rd);
+        const M43 Wi = loadM43(O->inv);
+        V3 v1 = transform43(ro, Wi);
+        V3 v2 = transform43(rdp, Wi);
+        V3 dd = normalize(sub(v2, v1));
+        rOk = finite3(v1) && finite3(dd);  // a non-finite ray fails every triangle test (NaN comparisons)
+        if (rOk) r = prepRay(v1, dd);
+    }
+    if (!rOk) return;
+    const int ms = om.x, mc = om.y;
     for (int mi = 0; mi < mc; mi++) {
         int meshId = __ldg(&S.objMeshIds[ms + mi]);
         const DevMesh* __restrict__ M = &S.meshes[meshId];
@@ -493,10 +501,14 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
             Hit lh;
             lh.obj = lh.mesh = lh.tri = -1; lh.key = 0; lh.u = lh.v = lh.d = 0.0f;
             int lkey = 0;
+            int cls = -1;
+            RayPre ro_;   // object-space ray of the transform class seen last
+            ro_.o = ro_.d = ro_.inv = mk(0.0f, 0.0f, 0.0f); ro_.par = ro_.oct = 0;
+            bool roOk = false;
             for (int i = 0; i < w1; i++) {
                 const float before = ld;
                 const bool fb = lf;
-                objectQuery<COUNT, LEAFONLY>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr);
+                objectQuery<COUNT, LEAFONLY>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr, cls, ro_, roOk);
                 if (lf && (!fb || ld < before)) lkey = w0 + i;
             }
             if (lf) {

@@ -147,16 +147,23 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
                 const float4 o4 = J.rayO[slot], d4 = J.rayD[slot];
                 const int2 ig = J.rayIgn[slot];
                 const V3 wo = mk(o4.x, o4.y, o4.z), wd = mk(d4.x, d4.y, d4.z);
+                int cls = -1;
+                bool rOk = false;
                 do {
                     const int2 pr = __ldg(&S.pairs[pi]);
                     const DevObj* __restrict__ O = &S.objs[pr.x];
-                    // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (OctreeSpatialManager.cs:358-364)
-                    const M43 Wi = loadM43(O->inv);
-                    const V3 v1 = transform43(wo, Wi);
-                    const V3 v2 = transform43(add(wo, wd), Wi);
-                    const V3 dd = normalize(sub(v2, v1));
-                    if (!finite3(v1) || !finite3(dd)) { pi++; continue; }
-                    r = prepRay(v1, dd);
+                    const int oc = __ldg(&O->xformClass);
+                    if (oc != cls) {   // objects with bit-identical InverseWorld share the object-space ray
+                        cls = oc;
+                        // v1 = P * W^-1 ; v2 = (P + D) * W^-1 ; D' = Normalize(v2 - v1)   (OctreeSpatialManager.cs:358-364)
+                        const M43 Wi = loadM43(O->inv);
+                        const V3 v1 = transform43(wo, Wi);
+                        const V3 v2 = transform43(add(wo, wd), Wi);
+                        const V3 dd = normalize(sub(v2, v1));
+                        rOk = finite3(v1) && finite3(dd);
+                        if (rOk) r = prepRay(v1, dd);
+                    }
+                    if (!rOk) { pi++; continue; }
                     const DevMesh* __restrict__ M = &S.meshes[pr.y];
                     if (COUNT) ctr.nBox++;
                     if (!meshBoxSlab(M, r)) { pi++; continue; }

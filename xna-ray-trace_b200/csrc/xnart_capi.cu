@@ -98,6 +98,7 @@ struct XnartCtx {
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
     int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
+    int64_t totalRefs = 0;   // leaf references of all mesh octrees
     std::atomic<int64_t> launches{0};
     XnartCounters last{};
 };
@@ -406,7 +407,10 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         DevObj& d = dobjs[i];
         std::memcpy(d.world, o.world, 64);
         std::memcpy(d.inv, o.inv, 64);
-        d.meshStart = (int)om; d.meshCount = (int)o.meshIds.size(); d._pad[0] = d._pad[1] = 0;
+        d.meshStart = (int)om; d.meshCount = (int)o.meshIds.size(); d._pad = 0;
+        d.xformClass = (int)i;
+        for (size_t j = 0; j < i; j++)
+            if (std::memcmp(c->objs[j].inv, o.inv, 64) == 0) { d.xformClass = dobjs[j].xformClass; break; }
         for (int id : o.meshIds) objMeshIds[om++] = id;
     }
     // (object, mesh) pairs in visiting order when the scene octree is one leaf (wavefront path)
@@ -418,6 +422,7 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         }
     }
     c->nPairs = (int)pairs.size();
+    c->totalRefs = (int64_t)nMeshRefs;
     for (DeviceState& d : c->devs) {
         CU_TRY(c, cudaSetDevice(d.dev));
         CU_TRY(c, cudaStreamSynchronize(d.stream));
@@ -549,7 +554,9 @@ static bool useWave(const XnartCtx* c, const DeviceState& d) {
     if (c->nPairs <= 0 || d.traceBlocks <= 0 || d.traceBlocksCount <= 0) return false;
     if (c->traversalMode == 1) return false;
     if (c->traversalMode == 2) return true;
-    return deepScene(c);
+    // small meshes (e.g. the 960-triangle spheres of the reference's default scene) do not have the
+    // heavy-tailed queries the persistent kernel is for, and its fixed launch sequence costs more there
+    return deepScene(c) && c->totalRefs >= 65536;
 }
 
 static int validateFrame(XnartCtx* c, const XnartFrame* f) {
