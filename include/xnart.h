@@ -167,6 +167,13 @@ int32_t xnart_render_frame_device(XnartCtx* ctx, const XnartFrame* frame,
  * the device->host copy of a frame overlaps the rendering of the next. */
 int32_t xnart_render_frames(XnartCtx* ctx, const XnartFrame* frames, int32_t n, uint32_t* rgba8Out);
 
+/* The ray casts of adaptive multisampling (RayTracer.GetColorForQuadrant, RayTracer.cs:215-311): for each
+ * of n screen positions (x, y) — viewport pixel units, sub-pixel positions allowed — Unproject
+ * (x, y, 0) and (x, y, 1), normalise, CastRay at iteration 0 (:220-276); rgba8Out[i] is the Color.
+ * The refinement decision around the casts (:279-309) is host logic. */
+int32_t xnart_cast_rays(XnartCtx* ctx, const XnartFrame* frame, const float* screenXY, int64_t n,
+                        uint32_t* rgba8Out);
+
 /* Batch form of ISpatialManager.GetRayIntersection (ISpatialManager.cs:15;
  * OctreeSpatialManager.cs:312-455) for parity testing: rays6 = n x (position xyz, direction
  * xyz); ignoreMeshTri2 = n x (meshId, triangleId) or NULL (-1,-1 = nothing ignored).

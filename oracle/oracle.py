@@ -118,6 +118,18 @@ class Oracle:
         self._check(self._l.xo_render_rows(self._h, C.byref(frame), _p(out), C.c_int32(n_threads), C.c_int32(y0), C.c_int32(y1)))
         return out
 
+    def render_frame_multisample(self, frame, quality, n_threads=1):
+        """RayTracer.RenderInternalWithMultisampling (RayTracer.cs:128-311)."""
+        out = np.zeros((frame.vpH, frame.vpW), dtype=np.uint32)
+        self._check(self._l.xo_render_frame_multisample(self._h, C.byref(frame), C.c_int32(quality), _p(out), C.c_int32(n_threads)))
+        return out
+
+    def cast_samples(self, frame, xy):
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros(len(xy), dtype=np.uint32)
+        self._check(self._l.xo_cast_samples(self._h, C.byref(frame), _p(xy), C.c_int64(len(xy)), _p(out)))
+        return out
+
     def trace_rays(self, rays6, ignore=None):
         rays6 = np.ascontiguousarray(rays6, dtype=np.float32).reshape(-1, 6)
         n = len(rays6)

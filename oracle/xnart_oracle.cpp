@@ -870,6 +870,100 @@ int32_t xo_render_frame(XoCtx* h, const XnartFrame* f, uint32_t* out, int32_t nT
     return xo_render_rows(h, f, out, nThreads, 0, f->vpH);
 }
 
+// ------------------------------------------------------------------------------------------
+// Adaptive multisampling — RayTracer.RenderInternalWithMultisampling / RenderFirstPass /
+// GetColorForQuadrant (RayTracer.cs:128-311), literal restatement including the :305 slip (the
+// refined lower-right quadrant is stored into urColor, lrColor keeps its sample).
+// ------------------------------------------------------------------------------------------
+static Ray sampleRay(const XnartFrame& f, const M4& inv, float sx, float sy) {
+    Viewport vp{f.vpX, f.vpY, f.vpW, f.vpH, f.minDepth, f.maxDepth};
+    Ray r;
+    r.p = unprojectWithInverse(vp, V3{sx, sy, 0.0f}, inv);     // :224-227
+    V3 v2 = unprojectWithInverse(vp, V3{sx, sy, 1.0f}, inv);    // :229-230
+    r.d = normalize(sub(v2, r.p));                              // :231-232
+    return r;
+}
+
+static uint32_t colorForQuadrant(const Ctx& c, const FrameParams& fp, const XnartFrame& f, const M4& inv, float centerX, float centerY,
+                                 float size, int iteration, int quality, LocalCounters& lc) {
+    const float TRESHOLD = 0.5f;                                  // :340
+    const float quarterSize = size * 0.25f;                       // :218
+    const float xs[4] = {centerX - quarterSize, centerX + quarterSize, centerX - quarterSize, centerX + quarterSize};
+    const float ys[4] = {centerY - quarterSize, centerY - quarterSize, centerY + quarterSize, centerY + quarterSize};
+    uint32_t col[4];                                              // ul, ur, ll, lr
+    for (int k = 0; k < 4; k++) {
+        Ray r = sampleRay(f, inv, xs[k], ys[k]);
+        lc.raysPrimary++;
+        col[k] = castRay(c, fp, r, 0, -1, -1, 1.0f, lc);          // :234, 248, 262, 276
+    }
+    if (iteration < quality) {                                    // :279
+        V3 v[4];
+        for (int k = 0; k < 4; k++) v[k] = unpackColor(col[k]);
+        V3 average = divs(add(add(add(v[0], v[1]), v[2]), v[3]), 4.0f);   // :285
+        float averageLength = length(average);
+        const float half = size / 2.0f;
+        if (std::fabs(averageLength - length(v[0])) > TRESHOLD)
+            col[0] = colorForQuadrant(c, fp, f, inv, centerX - quarterSize, centerY - quarterSize, half, iteration + 1, quality, lc);
+        if (std::fabs(averageLength - length(v[1])) > TRESHOLD)
+            col[1] = colorForQuadrant(c, fp, f, inv, centerX + quarterSize, centerY - quarterSize, half, iteration + 1, quality, lc);
+        if (std::fabs(averageLength - length(v[2])) > TRESHOLD)
+            col[2] = colorForQuadrant(c, fp, f, inv, centerX - quarterSize, centerY + quarterSize, half, iteration + 1, quality, lc);
+        if (std::fabs(averageLength - length(v[3])) > TRESHOLD)   // :303-306: the result lands in urColor
+            col[1] = colorForQuadrant(c, fp, f, inv, centerX + quarterSize, centerY + quarterSize, half, iteration + 1, quality, lc);
+    }
+    V3 sum = add(add(add(unpackColor(col[0]), unpackColor(col[1])), unpackColor(col[2])), unpackColor(col[3]));
+    return packColor(divs(sum, 4.0f), fp.semantics);              // :309
+}
+
+// CastRay for arbitrary screen-space sample positions (the four casts of GetColorForQuadrant, :220-276).
+int32_t xo_cast_samples(XoCtx* h, const XnartFrame* f, const float* xy, int64_t n, uint32_t* out) {
+    Ctx& c = h->c;
+    if (!c.built) { c.err = "scene not built"; return XNART_ERR_NOT_BUILT; }
+    const int savedSem = c.semantics;
+    c.semantics = f->semantics;
+    FrameParams fp{f->maxReflections, f->filtering, f->addressMode, f->semantics};
+    const M4 inv = frameInverse(*f);
+    LocalCounters lc;
+    for (int64_t i = 0; i < n; i++) {
+        Ray r = sampleRay(*f, inv, xy[2 * i], xy[2 * i + 1]);
+        out[i] = castRay(c, fp, r, 0, -1, -1, 1.0f, lc);
+    }
+    c.semantics = savedSem;
+    return 0;
+}
+
+int32_t xo_render_frame_multisample(XoCtx* h, const XnartFrame* f, int32_t quality, uint32_t* out, int32_t nThreads) {
+    Ctx& c = h->c;
+    if (!c.built) { c.err = "scene not built"; return XNART_ERR_NOT_BUILT; }
+    resetCounters(c.counters);
+    const int savedSem = c.semantics;
+    c.semantics = f->semantics;
+    FrameParams fp{f->maxReflections, f->filtering, f->addressMode, f->semantics};
+    const M4 inv = frameInverse(*f);
+    std::atomic<int> scanline{-1};
+    const int W = f->vpW, H = f->vpH;
+    auto worker = [&]() {
+        LocalCounters lc;
+        for (;;) {
+            int y = ++scanline;
+            if (y >= H) break;
+            for (int x = 0; x < W; x++) {
+                lc.pixels++;
+                out[(size_t)y * (size_t)W + (size_t)x] = colorForQuadrant(c, fp, *f, inv, (float)x, (float)y, 1.0f, 0, quality, lc);  // :197
+            }
+        }
+        flush(c.counters, lc);
+    };
+    if (nThreads <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nThreads; i++) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    c.semantics = savedSem;
+    return 0;
+}
+
 int32_t xo_primary_rays(const XnartFrame* f, float* rays6) {
     const M4 inv = frameInverse(*f);
     for (int y = 0; y < f->vpH; y++)

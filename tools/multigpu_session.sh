@@ -7,7 +7,7 @@ done
 python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-deep-scene > gpurun_out/mg_bench_n1.log 2>/dev/null
 python tools/tilesplit.py grid 3840 2160 --frames 5 2>/dev/null | tail -1 > gpurun_out/mg_tile_grid4k_n1.log
 $TR --nproc-per-node 8 --master-port 29531 tools/flythrough.py --frames 600 2>/dev/null | tail -1 > gpurun_out/mg_fly_n8.log
-$TR --nproc-per-node 8 --master-port 29532 tools/tilesplit.py soup 1920 1080 --n 2000000 --frames 3 2>gpurun_out/mg_tile_soup_n8.err | tail -1 > gpurun_out/mg_tile_soup_n8.log
-python tools/tilesplit.py soup 1920 1080 --n 2000000 --frames 3 2>/dev/null | tail -1 > gpurun_out/mg_tile_soup_n1.log
+$TR --nproc-per-node 8 --master-port 29532 tools/tilesplit.py soup 1920 1080 --tris 2000000 --frames 3 2>gpurun_out/mg_tile_soup_n8.err | tail -1 > gpurun_out/mg_tile_soup_n8.log
+python tools/tilesplit.py soup 1920 1080 --tris 2000000 --frames 3 2>/dev/null | tail -1 > gpurun_out/mg_tile_soup_n1.log
 python tools/flythrough.py --frames 600 2>/dev/null | tail -1 > gpurun_out/mg_fly_n1.log
 tail -n 2 gpurun_out/mg_*.log | cut -c1-420

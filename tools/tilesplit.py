@@ -21,7 +21,7 @@ def main():
     ap.add_argument("scene", choices=["grid", "soup", "crate"])
     ap.add_argument("width", type=int)
     ap.add_argument("height", type=int)
-    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--tris", dest="n", type=int, default=None, help="triangle / grid-size parameter of the scene generator")
     ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--frames", type=int, default=5)
     ap.add_argument("--band-rows", type=int, default=8)

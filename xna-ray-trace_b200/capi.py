@@ -69,7 +69,7 @@ def lib():
 EXPORTS = [
     "xnart_create", "xnart_destroy", "xnart_last_error", "xnart_set_option", "xnart_add_mesh", "xnart_add_object",
     "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_render_frames",
-    "xnart_trace_rays",
+    "xnart_trace_rays", "xnart_cast_rays",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
     "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump",
 ]
@@ -180,6 +180,14 @@ class Xnart:
         assert out.dtype == np.uint32 and out.size == n * h * w and out.flags["C_CONTIGUOUS"]
         self._l.xnart_render_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         self._check(self._l.xnart_render_frames(self._h, C.cast(arr, C.c_void_p), C.c_int32(n), out.ctypes.data))
+        return out
+
+    def cast_rays(self, frame, screen_xy):
+        """xnart_cast_rays: CastRay through n screen positions (x, y); returns n packed colours."""
+        xy = np.ascontiguousarray(screen_xy, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros(len(xy), dtype=np.uint32)
+        self._l.xnart_cast_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        self._check(self._l.xnart_cast_rays(self._h, C.addressof(frame), xy.ctypes.data, C.c_int64(len(xy)), out.ctypes.data))
         return out
 
     def render_frame_device(self, frame, dev_ptr, stream=None):

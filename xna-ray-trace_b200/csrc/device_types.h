@@ -138,6 +138,9 @@ struct DevFrame {
     long long pixelBase;   // first shard-local pixel index of the chunk
     int chunkPixels;
     int tiled;             // 1: shard-local pixel indices run over 8x4 tiles (kernels.cu: pixelOf)
+    // xnart_cast_rays: primary rays through arbitrary screen positions (x, y) instead of pixel centres;
+    // "pixel" q is sample q and its colour goes to out[q]
+    const float2* samples;
 };
 
 // Per-render path arena (SoA over "path nodes": one node per traced primary/reflection/refraction ray).

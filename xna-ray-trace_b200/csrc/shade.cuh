@@ -18,6 +18,7 @@ __device__ __forceinline__ unsigned warpSum(unsigned v) {
 // Tiled frames deal pixels to warps as 8x4 tiles (32 consecutive indices = one tile), so the rays
 // of a warp start out close together and walk the same octree nodes; otherwise scanline order.
 __device__ __forceinline__ void pixelOf(const DevFrame& F, long long q, int& x, int& y) {
+    if (F.samples) { x = (int)q; y = 0; return; }   // sample batch: out[q]
     int lr;
     if (F.tiled) {
         const int rowW = 4 * F.vpW;
@@ -65,10 +66,17 @@ struct RayIn {
 __device__ __forceinline__ RayIn loadRay(const DevFrame& F, const DevArena& A, int level, unsigned idx) {
     RayIn r;
     if (level == 0) {
-        int x, y;
-        pixelOf(F, F.pixelBase + idx, x, y);
-        r.o = unproject(F, (float)x, (float)y, 0.0f);
-        V3 farP = unproject(F, (float)x, (float)y, 1.0f);
+        float sx, sy;
+        if (F.samples) {   // GetColorForQuadrant's sub-pixel positions (RayTracer.cs:220-232)
+            const float2 sp = F.samples[F.pixelBase + idx];
+            sx = sp.x; sy = sp.y;
+        } else {
+            int x, y;
+            pixelOf(F, F.pixelBase + idx, x, y);
+            sx = (float)x; sy = (float)y;
+        }
+        r.o = unproject(F, sx, sy, 0.0f);
+        V3 farP = unproject(F, sx, sy, 1.0f);
         r.d = normalize(sub(farP, r.o));
         r.ignM = -1; r.ignT = -1; r.refIndex = 1.0f;
     } else {

@@ -576,7 +576,8 @@ static int validateFrame(XnartCtx* c, const XnartFrame* f) {
 }
 
 // Enqueue the whole trace loop of one frame shard on `st`, writing full-frame-indexed RGBA8 to devOut.
-static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st, bool accumulate = false) {
+static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st, bool accumulate = false,
+                        const float2* devSamples = nullptr, long long nSamples = 0) {
     DevFrame F;
     {
         // Viewport.Unproject: Invert(Multiply(Multiply(world = Identity, view), proj)) — once per frame
@@ -593,8 +594,10 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     F.shardBandRows = f.shardCount > 1 ? f.shardBandRows : 1;
     F.nLights = (int)c->lights.size();
     F.tiled = 0;
+    F.samples = devSamples;
+    if (devSamples) { F.shardIndex = 0; F.shardCount = 1; F.shardBandRows = 1; }
     const int D = f.maxReflections;
-    const long long localPixels = (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
+    const long long localPixels = devSamples ? nSamples : (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
     d.lastPixels = accumulate ? d.lastPixels + localPixels : localPixels;
     d.lastLights = F.nLights;
     // worst-case arena per pixel: a chain of D+1 path nodes, or a full binary tree when a
@@ -611,7 +614,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     // 8x4 pixel tiles per warp when the shard is made of whole tiles (and so is every chunk)
     {
         const long long tileRow = 4LL * f.vpW;
-        const bool whole = (f.vpW % 8 == 0) && (localPixels % tileRow == 0);
+        const bool whole = !devSamples && (f.vpW % 8 == 0) && (localPixels % tileRow == 0);
         if (whole && chunk < localPixels && chunk >= tileRow) chunk -= chunk % tileRow;
         F.tiled = (whole && (chunk >= localPixels || chunk % tileRow == 0)) ? 1 : 0;
     }
@@ -953,6 +956,45 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
     rc = collectCounters(c);
     c->last.msCopy = 0; c->last.msTotal = msTotal;
     c->progress = 1.0f;
+    return rc;
+}
+
+// CastRay for arbitrary screen positions: what GetColorForQuadrant does four times per quadrant
+// (RayTracer.cs:220-276) — Unproject (x, y, 0) and (x, y, 1), normalise, CastRay at iteration 0.
+// screenXY = n x (x, y) in viewport pixel units (sub-pixel positions allowed), rgba8Out = n colours.
+// The adaptive refinement around it (RayTracer.cs:279-309) is host logic (host.py).
+int32_t xnart_cast_rays(XnartCtx* c, const XnartFrame* frame, const float* screenXY, int64_t n, uint32_t* out) {
+    if (!c || n < 0 || (n > 0 && (!screenXY || !out))) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_cast_rays: bad arguments");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
+    if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
+    int rc = validateFrame(c, frame);
+    if (rc != XNART_OK) return rc;
+    if (n > 0x7fffffffLL) return fail(c, XNART_ERR_UNSUPPORTED, "xnart_cast_rays: too many samples in one batch");
+    if (n == 0) return XNART_OK;
+    if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
+    DeviceState& d = c->devs[0];
+    CU_TRY(c, cudaSetDevice(d.dev));
+    float2* ds = nullptr;
+    uint32_t* dout = nullptr;
+    cudaError_t e = cudaMalloc(&ds, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ds, screenXY, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream);
+    if (e != cudaSuccess) { cudaFree(ds); cudaFree(dout); return fail(c, XNART_ERR_CUDA, std::string("xnart_cast_rays: ") + cudaGetErrorString(e)); }
+    rc = enqueueFrame(c, d, *frame, dout, d.stream, false, ds, n);
+    if (rc == XNART_OK) {
+        e = cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+        if (e != cudaSuccess) rc = fail(c, XNART_ERR_CUDA, std::string("xnart_cast_rays: ") + cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(d.stream);
+    }
+    cudaFree(ds); cudaFree(dout);
+    if (rc != XNART_OK) return rc;
+    c->last.msCopy = 0; c->last.msTotal = 0;
+    rc = collectCounters(c);
+    c->last.msTotal = c->last.msLevels + c->last.msResolve;
     return rc;
 }
 

@@ -222,12 +222,50 @@ class RayTracer:
         with self._lock:
             if self._busy:
                 raise InvalidOperationException("Cannot render while the ray tracer is busy.")  # RayTracer.cs:62-63
-            if self.UseMultisampling:
-                raise NotImplementedError("adaptive multisampling (RayTracer.cs:128-311) is outside the accelerated path")
             self._busy = True
         self._thread = threading.Thread(target=self._render_internal, name="RenderDispatcherThread", daemon=True)
         self._thread.start()
         return self._thread
+
+    # ---- adaptive multisampling (RayTracer.cs:128-311) -------------------------------------------
+    TRESHOLD = np.float32(0.5)  # RayTracer.cs:340
+
+    def _render_with_multisampling(self, be, frame, w, h):
+        """RenderInternalWithMultisampling / RenderFirstPass (RayTracer.cs:128-213): every pixel (x, y) gets
+        GetColorForQuadrant(x, y, 1.0f, 0).  The recursion is run level by level: all quadrants of one
+        iteration depth are cast as ONE batch through `xnart_cast_rays` (4 rays each), the refinement test
+        (:279-306) picks the quadrants of the next depth, and the colours are combined on the way back."""
+        ys, xs = np.mgrid[0:h, 0:w]
+        cx = xs.astype(np.float32).ravel()
+        cy = ys.astype(np.float32).ravel()
+        size = np.full(cx.shape, 1.0, dtype=np.float32)
+        return self._color_for_quadrants(be, frame, cx, cy, size, 0).reshape(h, w)
+
+    def _color_for_quadrants(self, be, frame, cx, cy, size, iteration):
+        """GetColorForQuadrant (RayTracer.cs:215-311) for arrays of quadrants of one iteration depth."""
+        from . import xna
+
+        n = len(cx)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        q = size * np.float32(0.25)                                        # quarterSize (:218)
+        sx = np.stack([cx - q, cx + q, cx - q, cx + q], axis=1)             # ul, ur, ll, lr (:221,237,251,265)
+        sy = np.stack([cy - q, cy - q, cy + q, cy + q], axis=1)
+        col = be.cast_rays(frame, np.stack([sx, sy], axis=2).reshape(-1, 2)).reshape(n, 4)
+        if iteration < self.MultisampleQuality:                             # :279
+            v = xna.color_to_vector3(col)                                   # (n, 4, 3)
+            average = (((v[:, 0] + v[:, 1]) + v[:, 2]) + v[:, 3]) * np.float32(0.25)   # Vector3 / 4.0f multiplies by 1f/4f
+            avg_len = xna.length3(average)
+            refine = np.abs(avg_len[:, None] - xna.length3(v)) > self.TRESHOLD         # (n, 4)
+            half = size / np.float32(2.0)
+            # the four recursive calls (:289-306); the result of the lower-right one is stored into urColor (:305)
+            for k, dst in ((0, 0), (1, 1), (2, 2), (3, 1)):
+                m = refine[:, k]
+                if m.any():
+                    col[m, dst] = self._color_for_quadrants(be, frame, sx[m, k], sy[m, k], half[m], iteration + 1)
+        v = xna.color_to_vector3(col)
+        total = ((v[:, 0] + v[:, 1]) + v[:, 2]) + v[:, 3]
+        return xna.color_from_vector3(total * np.float32(0.25))             # :309
 
     def Render(self):
         """Synchronous convenience: RenderAsync + wait."""
@@ -246,7 +284,10 @@ class RayTracer:
             if self.CurrentTarget is None or self.CurrentTarget.shape != (h, w):
                 self.CurrentTarget = np.zeros((h, w), dtype=np.uint32)
             try:
-                be.render_frame(frame, out=self.CurrentTarget)
+                if self.UseMultisampling:
+                    self.CurrentTarget[...] = self._render_with_multisampling(be, frame, w, h)
+                else:
+                    be.render_frame(frame, out=self.CurrentTarget)
             except capi.XnartError as e:
                 if e.code == 1:
                     raise ArgumentException(str(e))

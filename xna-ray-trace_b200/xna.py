@@ -168,3 +168,27 @@ def create_rotation_z(r):
 def aspect_ratio(width, height):
     """Viewport.AspectRatio = (float)Width / (float)Height."""
     return F(F(width) / F(height))
+
+
+# ---- Color (SURVEY.md A.2), vectorised over arrays of packed R | G<<8 | B<<16 | A<<24 colours ----
+def color_to_vector3(packed):
+    """Color.ToVector3(): (R/255f, G/255f, B/255f), each a binary32 division.  (..,) uint32 -> (.., 3) float32."""
+    p = np.asarray(packed, dtype=np.uint32)
+    ch = np.stack([p & 255, (p >> 8) & 255, (p >> 16) & 255], axis=-1).astype(np.float32)
+    return ch / np.float32(255.0)
+
+
+def color_from_vector3(v, truncate=False):
+    """new Color(Vector3), XNA 4.0: clamp(v * 255f) then round half to even (MonoGame: truncate); A = 255."""
+    t = np.asarray(v, dtype=np.float32) * np.float32(255.0)
+    t = np.where(np.isnan(t), np.float32(0.0), t)
+    t = np.clip(t, np.float32(0.0), np.float32(255.0))
+    q = (np.floor(t.astype(np.float64)) if truncate else np.rint(t.astype(np.float64))).astype(np.uint32)
+    return (q[..., 0] | (q[..., 1] << 8) | (q[..., 2] << 16) | np.uint32(0xFF000000)).astype(np.uint32)
+
+
+def length3(v):
+    """Vector3.Length(): (float)Math.Sqrt(((x*x) + (y*y)) + (z*z)), vectorised over (.., 3) float32."""
+    v = np.asarray(v, dtype=np.float32)
+    s = ((v[..., 0] * v[..., 0]) + (v[..., 1] * v[..., 1])) + (v[..., 2] * v[..., 2])
+    return np.sqrt(s.astype(np.float64)).astype(np.float32)
