@@ -130,6 +130,8 @@ class Oracle:
         self._check(self._l.xo_cast_samples(self._h, C.byref(frame), _p(xy), C.c_int64(len(xy)), _p(out)))
         return out
 
+    cast_rays = cast_samples   # same name as capi.Xnart.cast_rays: the oracle can stand in as a host-mirror backend
+
     def trace_rays(self, rays6, ignore=None):
         rays6 = np.ascontiguousarray(rays6, dtype=np.float32).reshape(-1, 6)
         n = len(rays6)

@@ -351,3 +351,28 @@ def test_split_queries_give_the_same_frames(X, oracle_mod):
         x.set_option(records.OPT_SPLIT_RAYS, 0)
         assert np.array_equal(a, x.render_frame(f2))
         x.close()
+
+
+@pytest.mark.parametrize("name", ["crate", "grid", "spheres"])
+def test_cast_rays_equals_oracle(X, oracle_mod, name):
+    """xnart_cast_rays: CastRay through arbitrary (sub-pixel) screen positions — the four casts of
+    GetColorForQuadrant (RayTracer.cs:220-276) — gives the oracle's colours."""
+    s = make_scene(name)
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart()
+    scenes.upload(x, s)
+    f = s.frame(160, 120, max_reflections=3)
+    rng = np.random.default_rng(4)
+    xy = rng.uniform(-2.0, 162.0, size=(20000, 2)).astype(np.float32)
+    xy[:, 1] *= 0.75
+    xy[:64] = np.stack(np.meshgrid(np.arange(8), np.arange(8)), -1).reshape(-1, 2)   # pixel centres as well
+    want, got = o.cast_samples(f, xy), x.cast_rays(f, xy)
+    assert np.array_equal(want, got) and len(np.unique(got)) > 20
+    assert x.cast_rays(f, np.zeros((0, 2), dtype=np.float32)).size == 0
+    # integer positions reproduce the frame's pixels
+    img = x.render_frame(f)
+    ys, xs = np.mgrid[0:120, 0:160]
+    px = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32)
+    assert np.array_equal(x.cast_rays(f, px).reshape(120, 160), img)
+    x.close()

@@ -77,13 +77,50 @@ def test_busy_contract(oracle_mod):
     tracer.Render()  # and it can render again afterwards
 
 
-def test_bad_model_and_multisampling():
+def test_bad_model():
     with pytest.raises(host.ArgumentException):
         host.SceneObject(["not a mesh"])
-    tr = host.RayTracer()
-    tr.UseMultisampling = True
-    with pytest.raises(NotImplementedError):
-        tr.RenderAsync()
+
+
+@pytest.mark.parametrize("quality", [0, 1, 2])
+def test_multisampling_host_logic_equals_literal_recursion(oracle_mod, quality):
+    """UseMultisampling (RayTracer.cs:128-311): the mirror runs GetColorForQuadrant level by level in batches
+    of ray casts; the oracle restates the recursion literally (including the :305 slip).  With the same ray
+    caster behind both, the frames must be identical — on the mirror's own scene and on the crate scene, whose
+    white ground against the black background makes the refinement test (:287-306) fire."""
+    size = (56, 40)
+    tracer = load_content(oracle_mod.Oracle(), size)
+    tracer.UseMultisampling = True
+    tracer.MultisampleQuality = quality
+    img = tracer.Render()
+    s = scenes.spheres_scene()
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    want = o.render_frame_multisample(s.frame(*size), quality, n_threads=4)
+    assert np.array_equal(img, want)
+    assert (want != o.render_frame(s.frame(*size), n_threads=4)).any()     # supersampling changes edge pixels
+
+    s = scenes.crate_scene()
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    f = s.frame(64, 48, max_reflections=2)
+    want = o.render_frame_multisample(f, quality, n_threads=4)
+    got = tracer._render_with_multisampling(o, f, 64, 48)
+    assert np.array_equal(got, want)
+    if quality > 0:
+        assert (want != o.render_frame_multisample(f, 0, n_threads=4)).any()   # refinement happened
+
+
+def test_color_helpers_match_oracle(oracle_mod):
+    rng = np.random.default_rng(1)
+    v = rng.uniform(-0.2, 1.2, size=(500, 3)).astype(np.float32)
+    v[0] = (0.5, 2.5 / 255.0, np.nan)
+    got = xna.color_from_vector3(v)
+    want = np.array([oracle_mod.pack_color(tuple(float(c) for c in row)) for row in v], dtype=np.uint32)
+    assert np.array_equal(got, want)
+    back = xna.color_to_vector3(got)
+    for i in (0, 7, 99):
+        assert np.array_equal(back[i], np.array(oracle_mod.unpack_color(int(got[i])), dtype=np.float32))
 
 
 @pytest.mark.gpu
@@ -93,6 +130,17 @@ def test_mirror_on_gpu(xnart_lib, oracle_mod):
     img = tracer.Render()
     assert np.array_equal(img, reference_image(oracle_mod, size))
     assert tracer.Progress == 1.0
+    # adaptive multisampling on the GPU ray caster == the oracle's literal recursion
+    tracer.Viewport = (96, 72)
+    tracer.CurrentCamera = host.Camera((0, 16, 32), (0, 0, 0), (0, 1, 0), math.pi / 4, xna.aspect_ratio(96, 72), 1.0, 1000.0)
+    tracer.UseMultisampling = True
+    tracer.MultisampleQuality = 2
+    ms = tracer.Render().copy()
+    s = scenes.spheres_scene()
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    assert np.array_equal(ms, o.render_frame_multisample(s.frame(96, 72), 2, n_threads=8))
+    tracer.UseMultisampling = False
     tracer.TextureFiltering = 9
     errs = []
     tracer.RenderCompleted.append(lambda s, e: errs.append(e))
