@@ -376,3 +376,68 @@ def test_cast_rays_equals_oracle(X, oracle_mod, name):
     px = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.float32)
     assert np.array_equal(x.cast_rays(f, px).reshape(120, 160), img)
     x.close()
+
+
+@pytest.mark.parametrize("schedule", SCHEDULES)
+def test_edge_cases(X, oracle_mod, schedule):
+    """Empty and degenerate inputs: a scene without objects, a mesh without triangles, a scene without lights,
+    a 1x1 viewport, a mesh of exactly itemTreshold and itemTreshold + 1 triangles (no split / one split,
+    MeshOctree.cs:86), and the deepest recursion the library accepts."""
+    def both(scene):
+        o = oracle_mod.Oracle()
+        scenes.upload(o, scene)
+        x = X.Xnart()
+        x.set_option(records.OPT_TRAVERSAL, schedule)
+        scenes.upload(x, scene)
+        return o, x
+
+    # no objects at all: every pixel is the background (RayTracer.cs:732)
+    s = scenes.SceneData("empty")
+    s.camera = scenes.CameraData((0.0, 2.0, 8.0), (0.0, 0.0, 0.0))
+    s.lights.append(scenes.spot_light((0.0, 5.0, 20.0)))
+    o, x = both(s)
+    f = s.frame(40, 24)
+    img = x.render_frame(f)
+    assert (img == 0xFF000000).all() and np.array_equal(img, o.render_frame(f))
+    assert (x.trace_rays(np.array([[0, 0, 5, 0, 0, -1]], dtype=np.float32))["tri"] == -1).all()
+    assert x.counters().hits == 0
+    x.close()
+
+    # an object whose mesh has no triangles, next to a real one
+    grid = make_scene("grid")
+    s = scenes.SceneData("hollow")
+    s.meshes.append(scenes.MeshData(scenes.make_triangles([], [], []), reflectiveness=0.5))
+    s.meshes.append(grid.meshes[0])
+    s.objects.append(scenes.ObjectData([0]))
+    s.objects.append(scenes.ObjectData([1]))
+    s.camera = grid.camera
+    s.max_reflections = 2
+    o, x = both(s)
+    f = s.frame(64, 40)
+    assert np.array_equal(x.render_frame(f), o.render_frame(f, n_threads=4))   # no lights: light sum 0 everywhere
+    from xna_ray_trace_b200 import xna
+
+    s.lights.append(scenes.directional_light(xna.normalize(xna.v3(0.3, 1.0, 0.2))))
+    x.set_lights(s.lights); o.set_lights(s.lights)
+    f1 = s.frame(1, 1)
+    assert np.array_equal(x.render_frame(f1), o.render_frame(f1))
+    f = s.frame(64, 40, max_reflections=29)      # kMaxLevels - 1
+    assert np.array_equal(x.render_frame(f), o.render_frame(f, n_threads=4))
+    with pytest.raises(X.XnartError):
+        x.render_frame(s.frame(8, 8, max_reflections=30))
+    x.close()
+
+    # 50 triangles stay one leaf, 51 split once (BuildTree: Count > itemTreshold)
+    for n_tri in (50, 51):
+        t = scenes.grid_triangles(8)[:n_tri]
+        s = scenes.SceneData("t%d" % n_tri)
+        s.meshes.append(scenes.MeshData(t, reflectiveness=0.3))
+        s.objects.append(scenes.ObjectData([0]))
+        s.lights.append(scenes.spot_light((0.0, 80.0, 40.0)))
+        s.camera = scenes.CameraData((0.0, 60.0, 90.0), (0.0, 0.0, 0.0))
+        s.max_reflections = 2
+        o, x = both(s)
+        assert x.tree(0)["depth"] == (0 if n_tri == 50 else 1)
+        f = s.frame(96, 64)
+        assert np.array_equal(x.render_frame(f), o.render_frame(f, n_threads=4))
+        x.close()

@@ -15,6 +15,8 @@
 // Two schedules of the same work: k_level walks one ray per thread (best when the octrees are a
 // leaf or two deep, e.g. the 14-triangle crate scene); k_level_coop lets the 8 lanes of an octet
 // walk each ray together (trace.cuh: traceMeshOctet), which keeps deep-tree traversal convergent.
+#include <algorithm>
+
 #include "kernels.h"
 #include "shade.cuh"
 
@@ -22,7 +24,10 @@
 #define XN_LEVEL_MIN_BLOCKS 2
 #endif
 #ifndef XN_LEAF_MIN_BLOCKS
-#define XN_LEAF_MIN_BLOCKS 3
+#define XN_LEAF_MIN_BLOCKS 6
+#endif
+#ifndef XN_LEAF_THREADS
+#define XN_LEAF_THREADS 128
 #endif
 #ifndef XN_DEEP_MIN_BLOCKS
 #define XN_DEEP_MIN_BLOCKS 4
@@ -84,8 +89,10 @@ __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, 
     }
 }
 
-template <bool COUNT, int MINB, bool LEAFONLY>
-__global__ void __launch_bounds__(256, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
+// THREADS x MINB fixes the register budget (128 x 6 or 256 x 3 -> 80 registers, 128 x 5 -> 96, 256 x 2 -> 128, 256 x 4 -> 64).
+// Measured on the 1080p crate frame (levels, ms): 128x6 0.404, 256x3 0.417, 128x5 0.415, 128x4 0.418, 192x3 0.438.
+template <bool COUNT, int MINB, bool LEAFONLY, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     Ctr ctr;
     ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
     unsigned nHits = 0, nRefl = 0, nRefr = 0;
@@ -251,8 +258,9 @@ cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A,
         if (count) k_level<true, XN_LEVEL_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
         else k_level<false, XN_LEVEL_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
     } else {                  // every MeshOctree a single leaf: no expansion code, no stack
-        if (count) k_level<true, XN_LEAF_MIN_BLOCKS, true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
-        else k_level<false, XN_LEAF_MIN_BLOCKS, true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+        const int g2 = (int)std::min<long long>((long long)grid * 256 / XN_LEAF_THREADS, 0x7fffffff);
+        if (count) k_level<true, XN_LEAF_MIN_BLOCKS, true, XN_LEAF_THREADS><<<g2, XN_LEAF_THREADS, 0, st>>>(S, F, A, lights, level);
+        else k_level<false, XN_LEAF_MIN_BLOCKS, true, XN_LEAF_THREADS><<<g2, XN_LEAF_THREADS, 0, st>>>(S, F, A, lights, level);
     }
     return cudaGetLastError();
 }
