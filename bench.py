@@ -52,17 +52,44 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs (B200_PROFILING.md).  The timed
+    regions here last a few milliseconds, so the samples come from NVML directly (pynvml, ~1 kHz) — one
+    `nvidia-smi` process start takes longer than the whole region; nvidia-smi is the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._nvml, self._h = None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        return [str(sm), str(self._max)] + [("Active" if mask & bit else "Not Active") for _, bit in self.BITS]
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                    self._stop.wait(0.001)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -86,7 +113,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def alg_bytes(c):
