@@ -225,8 +225,20 @@ def main():
     scene = scenes.crate_scene()
     x = capi.Xnart(devices=(local_rank,))
     scenes.upload(x, scene)
-    if os.environ.get("XNART_BENCH_FUSE") is not None:  # experiment switch: 0 = one launch per level instead of k_frame
+    if os.environ.get("XNART_BENCH_FUSE") is not None:  # experiment switch: 1 = k_frame instead of one launch per level
         x.set_option(records.OPT_FUSE_FRAME, int(os.environ["XNART_BENCH_FUSE"]))
+    # Frames in flight: a context renders one frame at a time on one stream (one path arena); INFLIGHT contexts
+    # on INFLIGHT streams render consecutive frames of the flythrough concurrently, so the kernels of one frame
+    # fill the launch gaps and the nearly empty deep levels of the other.
+    INFLIGHT = max(1, int(os.environ.get("XNART_BENCH_INFLIGHT", "3")))
+    ctxs = [x]
+    for _ in range(1, INFLIGHT):
+        xi = capi.Xnart(devices=(local_rank,))
+        scenes.upload(xi, scene)
+        if os.environ.get("XNART_BENCH_FUSE") is not None:
+            xi.set_option(records.OPT_FUSE_FRAME, int(os.environ["XNART_BENCH_FUSE"]))
+        ctxs.append(xi)
+    rstreams = [torch.cuda.Stream(device=dev) for _ in ctxs] if INFLIGHT > 1 else []
 
     # Frames are rendered into a ring of 2 x GROUP device buffers; every GROUP steps ONE async NCCL gather
     # ships the last GROUP frames of every rank to rank 0 (on NCCL's stream) while the next group is being
@@ -248,8 +260,13 @@ def main():
     all_frames = [scene.frame(W, H, camera=orbit_camera(scenes, i * world + rank)) for i in range(warm + args.steps)]
     state = {"n": 0}
 
+    def join_render_streams():
+        for rs in rstreams:
+            stream.wait_stream(rs)
+
     def flush_group(half):
         if world > 1:
+            join_render_streams()   # the collective is ordered after every frame of the group
             pending[half] = dist.gather(ring[half], gathered[half], dst=0, async_op=True)
 
     def step(i):
@@ -258,7 +275,13 @@ def main():
         if slot == 0 and pending[half] is not None:
             pending[half].wait()   # the render stream waits until this half's previous gather has finished
             pending[half] = None
-        x.render_frame_device(all_frames[i], ring[half, slot].data_ptr(), stream.cuda_stream)
+        if INFLIGHT > 1:
+            c = k % INFLIGHT
+            if slot < INFLIGHT:
+                rstreams[c].wait_stream(stream)   # buffer reuse / timing start are ordered through the main stream
+            ctxs[c].render_frame_device(all_frames[i], ring[half, slot].data_ptr(), rstreams[c].cuda_stream)
+        else:
+            x.render_frame_device(all_frames[i], ring[half, slot].data_ptr(), stream.cuda_stream)
         state["n"] = k + 1
         if slot == GROUP - 1:
             flush_group(half)
@@ -272,6 +295,7 @@ def main():
             if pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
+        join_render_streams()
 
     def barrier():
         drain()
@@ -283,7 +307,7 @@ def main():
         step(i)
     barrier()
     rays_per_step = []
-    launches0 = x.kernel_launches()
+    launches0 = sum(xi.kernel_launches() for xi in ctxs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -294,7 +318,7 @@ def main():
         ev1.record(stream)
         barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = x.kernel_launches() - launches0
+    launches = sum(xi.kernel_launches() for xi in ctxs) - launches0
     gather_ok = None
     if world > 1 and rank == 0:
         # every rank's frames must have landed on rank 0: different cameras -> different, non-empty frames
@@ -322,23 +346,40 @@ def main():
         total_rays = my_rays
     value = total_rays / (ms * 1e-3) / 1e6
 
-    # ---- e2e: the C-ABI call with host buffers (H2D of the frame description, D2H of the frame) ----
+    # ---- e2e: the C-ABI with HOST buffers.  Headline: the flythrough call xnart_render_frames — K frame
+    # descriptions in (184 B each), K finished frames out to page-locked host memory, everything inside the
+    # timed region; the context keeps INFLIGHT frames in flight and overlaps the device->host copies with the
+    # rendering of the next frames.  Beside it: K synchronous xnart_render_frame calls (one frame per call).
+    frames = all_frames[warm:]
+    E2E_BATCH = 32
+    xe = capi.Xnart(devices=(local_rank,), frames_in_flight=INFLIGHT)
+    scenes.upload(xe, scene)
+    pin_n = capi.PinnedFrame(H, W, frames=min(E2E_BATCH, max(1, len(frames))))
+    xe.render_frames(all_frames[:min(4, len(all_frames))], out=pin_n.array[:min(4, len(all_frames))])   # warm-up
+    barrier()
+    with ClockSampler(local_rank) as clocks2:
+        t0 = time.perf_counter()
+        for b0 in range(0, len(frames), E2E_BATCH):
+            chunk = frames[b0:b0 + E2E_BATCH]
+            xe.render_frames(chunk, out=pin_n.array[:len(chunk)])
+        e2e_s = time.perf_counter() - t0
+    checksum = int(pin_n.array[:len(frames[-E2E_BATCH:])].astype(np.uint64).sum()) if frames else 0
+    # one frame per call
     pin = capi.PinnedFrame(H, W)
     for i in range(3):
         x.render_frame(all_frames[i], out=pin)
-    barrier()
-    frames = all_frames[warm:]
-    with ClockSampler(local_rank) as clocks2:
-        t0 = time.perf_counter()
-        for f in frames:
-            x.render_frame(f, out=pin)
-        e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    for f in frames:
+        x.render_frame(f, out=pin)
+    e2e1_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, e2e1_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_rays / float(te[0]) / 1e6
-    checksum = int(pin.array.astype(np.uint64).sum())
+    e2e1_value = total_rays / float(te[1]) / 1e6
     clocks.rows += clocks2.rows  # both timed regions are short: pool their samples
+    xe.close()
+    pin_n.free()
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     # Shallow scenes: k_level, one launch per recursion level (D+1 per frame) + the resolve launches; the levels
@@ -432,11 +473,15 @@ def main():
             "config": {"workload": WORKLOAD, "width": W, "height": H, "max_reflections": scene.max_reflections,
                        "triangles": scene.n_triangles, "lights": len(scene.lights), "frames_per_step_per_gpu": 1,
                        "parallelism": ("frames sharded across GPUs (one per GPU per step); every %d steps one async NCCL gather ships the group to rank 0, overlapping the next frames" % GROUP) if world > 1 else "single GPU",
+                       "frames_in_flight": INFLIGHT,
                        "l2": "per-frame path arena (~0.9 GB) exceeds L2; a different camera every step"},
             "frames_per_s": world * args.steps / (ms * 1e-3),
             "rays_per_frame": total_rays / (world * max(1, args.steps)),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 184, "d2h_bytes_per_step": W * H * 4,
-                    "frames_per_s": world * args.steps / float(te[0]), "checksum": checksum},
+                    "frames_per_s": world * args.steps / float(te[0]), "checksum": checksum,
+                    "api": "xnart_render_frames (flythrough call, %d frames in flight per GPU, pinned host frames)" % INFLIGHT,
+                    "one_frame_per_call": {"value": e2e1_value, "frames_per_s": world * args.steps / float(te[1]),
+                                           "api": "xnart_render_frame, synchronous"}},
             "gpu_launches": int(launches),
             "gather_check": gather_ok,
             "clocks": clocks.summary(),
@@ -446,7 +491,8 @@ def main():
         }
         print(json.dumps(line))
     pin.free()
-    x.close()
+    for xi in ctxs:
+        xi.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -107,9 +107,12 @@ class PinnedFrame:
 class Xnart:
     """One libxnart context (`new RayTracer()` + scene, Game1.cs:98-138)."""
 
-    def __init__(self, devices=(0,)):
+    def __init__(self, devices=(0,), frames_in_flight=1):
+        """devices: CUDA device ids; frames_in_flight k > 1 lists every device k times, i.e. k independent
+        in-flight states per GPU for render_frames (see xnart_create in include/xnart.h)."""
         self._l = lib()
         self._h = C.c_void_p()
+        devices = tuple(devices) * max(1, int(frames_in_flight))
         n = len(devices)
         ids = (C.c_int32 * max(1, n))(*devices)
         rc = self._l.xnart_create(C.byref(self._h), C.c_int32(n), ids)

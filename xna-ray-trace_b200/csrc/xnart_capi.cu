@@ -790,7 +790,16 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
     if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
     c->progress = 0.0f;
     const size_t pixels = (size_t)frame->vpW * (size_t)frame->vpH;
-    const int nDev = (int)c->devs.size();
+    // One frame is split over DISTINCT GPUs only: a device id listed several times gives several in-flight
+    // states for xnart_render_frames (whole frames side by side); splitting one frame over them would only
+    // repeat the launch sequence on the same GPU.
+    std::vector<int> prim;
+    for (int i = 0; i < (int)c->devs.size(); i++) {
+        bool seen = false;
+        for (int j : prim) seen = seen || c->devs[j].dev == c->devs[i].dev;
+        if (!seen) prim.push_back(i);
+    }
+    const int nDev = (int)prim.size();
     // Is the caller's buffer page-locked?  Then the device->host copy can land in it directly.
     cudaPointerAttributes pa{};
     bool outPinned = (cudaPointerGetAttributes(&pa, out) == cudaSuccess) && pa.type == cudaMemoryTypeHost;
@@ -801,7 +810,7 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
     const bool callerShard = frame->shardCount > 1;
     if (callerShard && nDev > 1) return fail(c, XNART_ERR_UNSUPPORTED, "caller sharding with a multi-device context");
     for (int i = 0; i < nDev; i++) {
-        DeviceState& d = c->devs[i];
+        DeviceState& d = c->devs[prim[i]];
         CU_TRY(c, cudaSetDevice(d.dev));
         if (d.frameBufPixels < pixels) {
             CU_TRY(c, cudaStreamSynchronize(d.stream));
@@ -831,7 +840,7 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
     }
     double msTotal = 0, msCopy = 0;
     for (int i = 0; i < nDev; i++) {
-        DeviceState& d = c->devs[i];
+        DeviceState& d = c->devs[prim[i]];
         CU_TRY(c, cudaSetDevice(d.dev));
         CU_TRY(c, cudaStreamSynchronize(d.stream));
         c->progress = (float)(i + 1) / (float)nDev;
