@@ -179,6 +179,13 @@ int32_t xnart_render_frames(XnartCtx* ctx, const XnartFrame* frames, int32_t n, 
 int32_t xnart_cast_rays(XnartCtx* ctx, const XnartFrame* frame, const float* screenXY, int64_t n,
                         uint32_t* rgba8Out);
 
+/* xnart_render_frames with the frames left in device memory (n consecutive vpW*vpH frames at
+ * devRgba8Out), rendered by the in-flight states of the context's first GPU; ordered after the work
+ * already enqueued on cudaStream, which is made to wait for all of it (NULL: the call returns after
+ * completion).  For callers that gather the frames with a collective (one process per GPU). */
+int32_t xnart_render_frames_device(XnartCtx* ctx, const XnartFrame* frames, int32_t n,
+                                   void* devRgba8Out, void* cudaStream);
+
 /* Batch form of ISpatialManager.GetRayIntersection (ISpatialManager.cs:15;
  * OctreeSpatialManager.cs:312-455) for parity testing: rays6 = n x (position xyz, direction
  * xyz); ignoreMeshTri2 = n x (meshId, triangleId) or NULL (-1,-1 = nothing ignored).

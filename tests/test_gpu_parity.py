@@ -294,8 +294,25 @@ def test_render_frames_flythrough(X):
     assert x.counters().raysPrimary == 7 * 320 * 180
     pin = X.PinnedFrame(180, 320, frames=7)
     assert np.array_equal(single, x.render_frames(frames, out=pin.array))
-    pin.free()
     x.close()
+    # several frames in flight on one GPU (a device id listed k times): same frames, host and device output
+    import torch
+
+    x3 = X.Xnart(devices=(0,), frames_in_flight=3)
+    scenes.upload(x3, s)
+    assert np.array_equal(single, x3.render_frames(frames, out=pin.array))
+    assert np.array_equal(single[2], x3.render_frame(frames[2]))          # one frame is not split over the states
+    dev = torch.zeros((7, 180, 320), dtype=torch.int32, device="cuda:0")
+    x3.render_frames_device(frames, dev.data_ptr())
+    assert np.array_equal(single, dev.cpu().numpy().view(np.uint32))
+    st = torch.cuda.Stream()
+    dev.zero_()
+    torch.cuda.synchronize()
+    x3.render_frames_device(frames, dev.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(single, dev.cpu().numpy().view(np.uint32))
+    pin.free()
+    x3.close()
 
 
 def test_flythrough_into_avi_sink(X, tmp_path):

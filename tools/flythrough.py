@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--fps", type=float, default=30.0)   # Game1.cs:198
+    ap.add_argument("--in-flight", type=int, default=3, help="frames in flight per GPU")
     ap.add_argument("--out", default=None, help="AVI file written by rank 0 (omit to discard the frames)")
     args = ap.parse_args()
 
@@ -48,7 +49,7 @@ def main():
     else:
         s = scenes.crate_scene()
         cams = flythrough.orbit_cameras(args.frames, radius=72.0, height_y=35.0, target=(0.0, 11.8, 0.0))
-    x = capi.Xnart(devices=(local,))
+    x = capi.Xnart(devices=(local,), frames_in_flight=args.in_flight)
     scenes.upload(x, s)
     sink, mgr = None, None
     if rank == 0 and args.out:

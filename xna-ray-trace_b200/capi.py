@@ -69,7 +69,7 @@ def lib():
 EXPORTS = [
     "xnart_create", "xnart_destroy", "xnart_last_error", "xnart_set_option", "xnart_add_mesh", "xnart_add_object",
     "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_render_frames",
-    "xnart_trace_rays", "xnart_cast_rays",
+    "xnart_trace_rays", "xnart_cast_rays", "xnart_render_frames_device",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
     "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump",
 ]
@@ -184,6 +184,15 @@ class Xnart:
         self._l.xnart_render_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         self._check(self._l.xnart_render_frames(self._h, C.cast(arr, C.c_void_p), C.c_int32(n), out.ctypes.data))
         return out
+
+    def render_frames_device(self, frames, dev_ptr, stream=None):
+        """xnart_render_frames_device: n frames into n consecutive device frames at `dev_ptr`, all in-flight
+        states of the context working side by side; ordered on / joined into `stream`."""
+        n = len(frames)
+        arr = (XnartFrame * max(1, n))(*frames)
+        self._l.xnart_render_frames_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        self._check(self._l.xnart_render_frames_device(self._h, C.cast(arr, C.c_void_p), C.c_int32(n), C.c_void_p(dev_ptr),
+                                                       C.c_void_p(stream) if stream else None))
 
     def cast_rays(self, frame, screen_xy):
         """xnart_cast_rays: CastRay through n screen positions (x, y); returns n packed colours."""

@@ -968,6 +968,63 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
     return rc;
 }
 
+// xnart_render_frames with the output left on the device: n frames of one viewport size into n consecutive
+// device frames, dealt round-robin over the in-flight states of the context's first GPU (a device id listed k
+// times in xnart_create keeps k frames in flight).  The work is ordered after what is already enqueued on
+// `cudaStream` and the stream is made to wait for all of it, so the caller can chain a collective or a copy;
+// with a NULL stream the call returns after completion.
+int32_t xnart_render_frames_device(XnartCtx* c, const XnartFrame* frames, int32_t n, void* devOut, void* cudaStream) {
+    if (!c || n < 0 || (n > 0 && (!frames || !devOut))) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames_device: bad arguments");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
+    if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
+    if (n == 0) return XNART_OK;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        if ((rc = validateFrame(c, &frames[i])) != XNART_OK) return rc;
+        if (frames[i].vpW != frames[0].vpW || frames[i].vpH != frames[0].vpH || frames[i].shardCount > 1)
+            return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames_device: all frames must share one viewport size and be unsharded");
+    }
+    if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
+    const size_t pixels = (size_t)frames[0].vpW * (size_t)frames[0].vpH;
+    std::vector<int> states;   // in-flight states on the GPU of the first entry
+    for (int i = 0; i < (int)c->devs.size(); i++)
+        if (c->devs[i].dev == c->devs[0].dev) states.push_back(i);
+    DeviceState& d0 = c->devs[0];
+    CU_TRY(c, cudaSetDevice(d0.dev));
+    cudaStream_t user = cudaStream ? (cudaStream_t)cudaStream : d0.stream;
+    // order the states' streams after the caller's stream (buffer reuse), then fan out
+    CU_TRY(c, cudaEventRecord(d0.evRendered[0], user));
+    for (int si : states) {
+        DeviceState& d = c->devs[si];
+        if (d.stream != user) CU_TRY(c, cudaStreamWaitEvent(d.stream, d0.evRendered[0], 0));
+        d.lastPixels = 0;
+        CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+        CU_TRY(c, cudaEventRecord(d.ev[0], d.stream));
+    }
+    for (int f = 0; f < n; f++) {
+        DeviceState& d = c->devs[states[(size_t)f % states.size()]];
+        rc = enqueueFrame(c, d, frames[f], (uint32_t*)devOut + (size_t)f * pixels, d.stream, /*accumulate=*/true);
+        if (rc != XNART_OK) return rc;
+    }
+    for (int si : states) {
+        DeviceState& d = c->devs[si];
+        d.singleChunk = false; d.lastFused = false;
+        if (d.stream == user) continue;
+        CU_TRY(c, cudaEventRecord(d.evRendered[1], d.stream));
+        CU_TRY(c, cudaStreamWaitEvent(user, d.evRendered[1], 0));
+    }
+    if (!cudaStream) {
+        CU_TRY(c, cudaStreamSynchronize(user));
+        c->last.msCopy = 0; c->last.msTotal = 0;
+        rc = collectCounters(c);
+        c->last.msTotal = c->last.msLevels;
+    }
+    c->progress = 1.0f;
+    return rc;
+}
+
 // CastRay for arbitrary screen positions: what GetColorForQuadrant does four times per quadrant
 // (RayTracer.cs:220-276) — Unproject (x, y, 0) and (x, y, 1), normalise, CastRay at iteration 0.
 // screenXY = n x (x, y) in viewport pixel units (sub-pixel positions allowed), rgba8Out = n colours.

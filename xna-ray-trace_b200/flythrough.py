@@ -95,10 +95,10 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
         if pending[half] is not None:
             deliver(half)
         cnt = min(batch, rounds - g0)
-        for k in range(cnt):
-            f = (g0 + k) * world + rank
-            if f < n:
-                x.render_frame_device(scene.frame(width, height, camera=cameras[f]), ring[half, k].data_ptr(), stream.cuda_stream)
+        fl = [(g0 + k) * world + rank for k in range(cnt)]
+        fl = [f for f in fl if f < n]      # a rank's frames of a group are consecutive slots 0..len-1
+        if fl:
+            x.render_frames_device([scene.frame(width, height, camera=cameras[f]) for f in fl], ring[half].data_ptr(), stream.cuda_stream)
         work = dist.gather(ring[half], recv[half], dst=0, async_op=True) if world > 1 else None
         pending[half] = (work, g0, cnt)
     for h in sorted([h for h in range(2) if pending[h] is not None], key=lambda h: pending[h][1]):
