@@ -432,16 +432,15 @@ def main():
         if world == 1 and not args.no_deep_scene:
             # second target of BASELINE.json's north_star: the 1M-triangle octree scene (configs[2] geometry) at 1080p
             gs = scenes.grid_scene(707)
-            xg = capi.Xnart(devices=(local_rank,))
+            xg = capi.Xnart(devices=(local_rank,), frames_in_flight=INFLIGHT)
             scenes.upload(xg, gs)
-            gframes = [gs.frame(W, H, camera=scenes.CameraData((np.sin(0.13 * i) * 80.0, 40.0, np.cos(0.13 * i) * 80.0), (0.0, 0.0, 0.0))) for i in range(6)]
-            for f in gframes[:2]:
-                xg.render_frame_device(f, frame_dev.data_ptr(), None)
+            gframes = [gs.frame(W, H, camera=scenes.CameraData((np.sin(0.13 * i) * 80.0, 40.0, np.cos(0.13 * i) * 80.0), (0.0, 0.0, 0.0))) for i in range(12)]
+            gbuf = torch.zeros((len(gframes), H, W), dtype=torch.int32, device=dev)
+            xg.render_frames_device(gframes[:3], gbuf.data_ptr(), stream.cuda_stream)
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             g0.record(stream)
-            for f in gframes:
-                xg.render_frame_device(f, frame_dev.data_ptr(), stream.cuda_stream)
+            xg.render_frames_device(gframes, gbuf.data_ptr(), stream.cuda_stream)   # INFLIGHT frames side by side
             g1.record(stream)
             torch.cuda.synchronize()
             gms = g0.elapsed_time(g1) / len(gframes)
@@ -453,7 +452,8 @@ def main():
                                         2 * (gs.max_reflections + 1), "k_trace")
             deep = {"workload": "grid_1M_triangles_1080p_depth%d" % gs.max_reflections, "triangles": gs.n_triangles,
                     "lights": len(gs.lights), "value": float(np.mean(grays)) / (gms * 1e-3) / 1e6, "unit": "Mrays/s",
-                    "ms_per_frame": gms, "frames_per_s": 1e3 / gms, "rays_per_frame": float(np.mean(grays)), "roofline": groof}
+                    "ms_per_frame": gms, "frames_per_s": 1e3 / gms, "rays_per_frame": float(np.mean(grays)), "frames_in_flight": INFLIGHT,
+                    "roofline": groof}
             xg.close()
 
         if world == 1 and not args.no_cpu_baseline:
