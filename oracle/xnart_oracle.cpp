@@ -13,6 +13,7 @@
 //
 // Reference lines followed (paths relative to /root/reference):
 //   ray generation      RayTraceProject/RayTraceProject/RayTracer.cs:391-429
+//   multisampling       RayTraceProject/RayTraceProject/RayTracer.cs:128-311
 //   CastRay / shadows   RayTraceProject/RayTraceProject/RayTracer.cs:465-502, 506-737
 //   scene octree        RayTraceProject/RayTraceProject/Spatial/OctreeSpatialManager.cs:64-99, 218-248, 312-482
 //   mesh octree         RayTracerTypeLibrary/MeshOctree.cs:56-96, 204-236, 259-353

@@ -109,6 +109,11 @@ def test_multisampling_host_logic_equals_literal_recursion(oracle_mod, quality):
     assert np.array_equal(got, want)
     if quality > 0:
         assert (want != o.render_frame_multisample(f, 0, n_threads=4)).any()   # refinement happened
+        # the :305 slip (refined lower-right colour stored into urColor) is part of the contract and is exercised
+        # here: the "repaired" recursion gives a different frame
+        tracer.LR_DESTINATION = 3
+        assert (tracer._render_with_multisampling(o, f, 64, 48) != want).any()
+        tracer.LR_DESTINATION = 1
 
 
 def test_color_helpers_match_oracle(oracle_mod):

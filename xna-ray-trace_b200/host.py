@@ -229,6 +229,7 @@ class RayTracer:
 
     # ---- adaptive multisampling (RayTracer.cs:128-311) -------------------------------------------
     TRESHOLD = np.float32(0.5)  # RayTracer.cs:340
+    LR_DESTINATION = 1          # RayTracer.cs:305 stores the refined lower-right colour into urColor (index 1), not lrColor (3)
 
     def _render_with_multisampling(self, be, frame, w, h):
         """RenderInternalWithMultisampling / RenderFirstPass (RayTracer.cs:128-213): every pixel (x, y) gets
@@ -259,7 +260,7 @@ class RayTracer:
             refine = np.abs(avg_len[:, None] - xna.length3(v)) > self.TRESHOLD         # (n, 4)
             half = size / np.float32(2.0)
             # the four recursive calls (:289-306); the result of the lower-right one is stored into urColor (:305)
-            for k, dst in ((0, 0), (1, 1), (2, 2), (3, 1)):
+            for k, dst in ((0, 0), (1, 1), (2, 2), (3, self.LR_DESTINATION)):
                 m = refine[:, k]
                 if m.any():
                     col[m, dst] = self._color_for_quadrants(be, frame, sx[m, k], sy[m, k], half[m], iteration + 1)
