@@ -426,7 +426,7 @@ def main():
         if os.environ.get("XNART_BENCH_FUSE") == "1":
             roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_frame<false> (levels phase of the fused frame kernel)", 1, "k_frame")
         else:
-            roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_level<false, 2> (one launch per recursion level)",
+            roof, _, _ = roofline_of(x, all_frames[warm:warm + min(4, args.steps)], "k_level<false, 6, leaf-only, 128 threads> (one launch per recursion level)",
                                      scene.max_reflections + 1, "k_level")
 
         if world == 1 and not args.no_deep_scene:
