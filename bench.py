@@ -354,7 +354,7 @@ def main():
     E2E_BATCH = 32
     xe = capi.Xnart(devices=(local_rank,), frames_in_flight=INFLIGHT)
     scenes.upload(xe, scene)
-    pin_n = capi.PinnedFrame(H, W, frames=min(E2E_BATCH, max(1, len(frames))))
+    pin_n = capi.PinnedFrame(H, W, frames=max(4, min(E2E_BATCH, len(frames))))
     xe.render_frames(all_frames[:min(4, len(all_frames))], out=pin_n.array[:min(4, len(all_frames))])   # warm-up
     barrier()
     with ClockSampler(local_rank) as clocks2:
