@@ -250,10 +250,28 @@ def main():
     pending = [None, None]
     stream = torch.cuda.current_stream()
 
-    # The finished frames reach rank 0 through one async dist.gather per group (NCCL over NVLink).  Measured
-    # alternative (round 1, 8 GPUs): peer-to-peer copies into IPC-shared buffers of rank 0 through torch were
-    # 2.3x slower per step than the collective; capping NCCL's point-to-point channels did not help either.
-    gathered = [[torch.zeros((GROUP, H, W), dtype=torch.int32, device=dev) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    # How the finished frames reach rank 0, once per group of GROUP steps (XNART_BENCH_GATHER):
+    #   "nccl"  one async dist.gather (NCCL over NVLink); its receive kernels on rank 0 share the SMs with rank 0's
+    #           own rendering.
+    #   "p2p"   every rank copies its group straight into a receive buffer of rank 0 (CUDA IPC handle from
+    #           xnart_ipc_export, device-to-device xnart_copy_async on a copy stream: copy engines, no SMs); a
+    #           one-element all-reduce ordered after the copy is the completion signal.
+    gather_mode = os.environ.get("XNART_BENCH_GATHER", "nccl") if world > 1 else "none"
+    gathered = [None, None]
+    recv_ptr, remote_ptr = [None, None], [None, None]
+    half_bytes = GROUP * H * W * 4
+    copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if gather_mode == "p2p":
+        box = [None]
+        if rank == 0:
+            recv_ptr = [capi.alloc_device(local_rank, world * half_bytes) for _ in range(2)]
+            box[0] = [capi.ipc_export(local_rank, p) for p in recv_ptr]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            remote_ptr = [capi.ipc_open(local_rank, h) for h in box[0]]
+    elif gather_mode == "nccl":
+        gathered = [[torch.zeros((GROUP, H, W), dtype=torch.int32, device=dev) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
 
     warm = max(args.warmup, 3)
     # camera matrices are host-side inputs (Camera.View/Projection in the reference): built up front
@@ -265,9 +283,17 @@ def main():
             stream.wait_stream(rs)
 
     def flush_group(half):
-        if world > 1:
-            join_render_streams()   # the collective is ordered after every frame of the group
+        if world == 1:
+            return
+        join_render_streams()   # the transfer is ordered after every frame of the group
+        if gather_mode == "nccl":
             pending[half] = dist.gather(ring[half], gathered[half], dst=0, async_op=True)
+            return
+        copy_stream.wait_stream(stream)
+        dst = (recv_ptr if rank == 0 else remote_ptr)[half] + rank * half_bytes
+        capi.copy_async(local_rank, dst, ring[half].data_ptr(), half_bytes, copy_stream.cuda_stream)
+        with torch.cuda.stream(copy_stream):
+            pending[half] = dist.all_reduce(flag, async_op=True)   # done => every rank's group has landed
 
     def step(i):
         k = state["n"]
@@ -323,7 +349,12 @@ def main():
     if world > 1 and rank == 0:
         # every rank's frames must have landed on rank 0: different cameras -> different, non-empty frames
         last = ((state["n"] // GROUP) - 1) & 1
-        g = torch.stack(gathered[last])
+        if gather_mode == "p2p":
+            g = torch.zeros((world, GROUP, H, W), dtype=torch.int32, device=dev)
+            capi.copy_async(local_rank, g.data_ptr(), recv_ptr[last], world * half_bytes, stream.cuda_stream)
+            torch.cuda.synchronize()
+        else:
+            g = torch.stack(gathered[last])
         sums = [int(g[r, 0].to(torch.int64).bitwise_and(0xFFFFFF).sum().item()) for r in range(world)]
         gather_ok = all(v > 0 for v in sums) and len(set(sums)) == world
     # rays per frame (device counters are per render; re-render each timed camera outside the timed region)
@@ -472,7 +503,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "max_reflections": scene.max_reflections,
                        "triangles": scene.n_triangles, "lights": len(scene.lights), "frames_per_step_per_gpu": 1,
-                       "parallelism": ("frames sharded across GPUs (one per GPU per step); every %d steps one async NCCL gather ships the group to rank 0, overlapping the next frames" % GROUP) if world > 1 else "single GPU",
+                       "parallelism": ("frames sharded across GPUs (one per GPU per step); every %d steps the group is shipped to rank 0 (%s), overlapping the next frames" % (GROUP, "device-to-device copies into an IPC-shared buffer of rank 0 + 1-element all-reduce" if gather_mode == "p2p" else "async NCCL gather")) if world > 1 else "single GPU",
                        "frames_in_flight": INFLIGHT,
                        "l2": "per-frame path arena (~0.9 GB) exceeds L2; a different camera every step"},
             "frames_per_s": world * args.steps / (ms * 1e-3),
@@ -491,6 +522,15 @@ def main():
         }
         print(json.dumps(line))
     pin.free()
+    if gather_mode == "p2p":
+        torch.cuda.synchronize()
+        if rank != 0:
+            for ptr in remote_ptr:
+                capi.ipc_close(local_rank, ptr)
+        dist.barrier()
+        if rank == 0:
+            for ptr in recv_ptr:
+                capi.free_device(local_rank, ptr)
     for xi in ctxs:
         xi.close()
     if world > 1:

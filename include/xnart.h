@@ -186,6 +186,17 @@ int32_t xnart_cast_rays(XnartCtx* ctx, const XnartFrame* frame, const float* scr
 int32_t xnart_render_frames_device(XnartCtx* ctx, const XnartFrame* frames, int32_t n,
                                    void* devRgba8Out, void* cudaStream);
 
+/* Device-memory utilities for one-process-per-GPU gathers of finished frames (no reference counterpart:
+ * the reference is single-process).  Rank 0 allocates a receive buffer and exports a CUDA IPC handle; the
+ * other ranks open it on their own device and copy their frames into it with xnart_copy_async on their
+ * own streams (device-to-device over NVLink through the copy engines). */
+void*   xnart_alloc_device(int32_t device, int64_t bytes);
+void    xnart_free_device(int32_t device, void* devPtr);
+int32_t xnart_ipc_export(int32_t device, const void* devPtr, uint8_t handle64[64]);
+int32_t xnart_ipc_open(int32_t device, const uint8_t handle64[64], void** devPtrOut);
+int32_t xnart_ipc_close(int32_t device, void* devPtr);
+int32_t xnart_copy_async(int32_t device, void* dst, const void* src, int64_t bytes, void* cudaStream);
+
 /* Batch form of ISpatialManager.GetRayIntersection (ISpatialManager.cs:15;
  * OctreeSpatialManager.cs:312-455) for parity testing: rays6 = n x (position xyz, direction
  * xyz); ignoreMeshTri2 = n x (meshId, triangleId) or NULL (-1,-1 = nothing ignored).

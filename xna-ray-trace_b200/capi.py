@@ -70,6 +70,7 @@ EXPORTS = [
     "xnart_create", "xnart_destroy", "xnart_last_error", "xnart_set_option", "xnart_add_mesh", "xnart_add_object",
     "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_render_frames",
     "xnart_trace_rays", "xnart_cast_rays", "xnart_render_frames_device",
+    "xnart_alloc_device", "xnart_free_device", "xnart_ipc_export", "xnart_ipc_open", "xnart_ipc_close", "xnart_copy_async",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
     "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump",
 ]
@@ -77,6 +78,58 @@ EXPORTS = [
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def alloc_device(device, nbytes):
+    L = lib()
+    L.xnart_alloc_device.restype = C.c_void_p
+    L.xnart_alloc_device.argtypes = [C.c_int32, C.c_int64]
+    p = L.xnart_alloc_device(device, nbytes)
+    if not p:
+        raise XnartError(7, "xnart_alloc_device failed")
+    return p
+
+
+def free_device(device, ptr):
+    L = lib()
+    L.xnart_free_device.argtypes = [C.c_int32, C.c_void_p]
+    L.xnart_free_device(device, ptr)
+
+
+def ipc_export(device, ptr):
+    """64-byte CUDA IPC handle of a buffer from alloc_device (bytes object; send it to the other ranks)."""
+    L = lib()
+    h = (C.c_uint8 * 64)()
+    L.xnart_ipc_export.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+    rc = L.xnart_ipc_export(device, ptr, h)
+    if rc != 0:
+        raise XnartError(rc, "xnart_ipc_export failed")
+    return bytes(h)
+
+
+def ipc_open(device, handle):
+    L = lib()
+    out = C.c_void_p()
+    buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+    L.xnart_ipc_open.argtypes = [C.c_int32, C.c_void_p, C.c_void_p]
+    rc = L.xnart_ipc_open(device, buf, C.byref(out))
+    if rc != 0:
+        raise XnartError(rc, "xnart_ipc_open failed")
+    return out.value
+
+
+def ipc_close(device, ptr):
+    L = lib()
+    L.xnart_ipc_close.argtypes = [C.c_int32, C.c_void_p]
+    L.xnart_ipc_close(device, ptr)
+
+
+def copy_async(device, dst, src, nbytes, stream=None):
+    L = lib()
+    L.xnart_copy_async.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    rc = L.xnart_copy_async(device, dst, src, nbytes, C.c_void_p(stream) if stream else None)
+    if rc != 0:
+        raise XnartError(rc, "xnart_copy_async failed")
 
 
 class PinnedFrame:

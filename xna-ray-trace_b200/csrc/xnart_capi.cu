@@ -1135,6 +1135,42 @@ float xnart_progress(XnartCtx* c) { return c ? c->progress.load() : 0.0f; }
 
 int64_t xnart_kernel_launches(XnartCtx* c) { return c ? c->launches.load() : 0; }
 
+// ---- device-memory utilities for one-process-per-GPU gathers ------------------------------------
+// Finished frames of the other ranks can be written straight into a buffer of rank 0 with
+// device-to-device copies over NVLink (copy engines, no SMs) instead of a collective whose receive
+// kernels compete with rank 0's own rendering: rank 0 allocates the buffer and exports a CUDA IPC
+// handle, the other ranks open it and copy into it on their own streams.
+void* xnart_alloc_device(int32_t device, int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaMemset(p, 0, (size_t)bytes);
+    return p;
+}
+void xnart_free_device(int32_t device, void* p) { if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p); }
+int32_t xnart_ipc_export(int32_t device, const void* devPtr, uint8_t handle64[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t h;
+    if (!devPtr || !handle64 || cudaSetDevice(device) != cudaSuccess || cudaIpcGetMemHandle(&h, const_cast<void*>(devPtr)) != cudaSuccess) { cudaGetLastError(); return XNART_ERR_CUDA; }
+    std::memcpy(handle64, &h, 64);
+    return XNART_OK;
+}
+int32_t xnart_ipc_open(int32_t device, const uint8_t handle64[64], void** devPtrOut) {
+    cudaIpcMemHandle_t h;
+    if (!handle64 || !devPtrOut) return XNART_ERR_INVALID_ARGUMENT;
+    std::memcpy(&h, handle64, 64);
+    if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(devPtrOut, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return XNART_ERR_CUDA; }
+    return XNART_OK;
+}
+int32_t xnart_ipc_close(int32_t device, void* devPtr) {
+    if (!devPtr || cudaSetDevice(device) != cudaSuccess || cudaIpcCloseMemHandle(devPtr) != cudaSuccess) { cudaGetLastError(); return XNART_ERR_CUDA; }
+    return XNART_OK;
+}
+int32_t xnart_copy_async(int32_t device, void* dst, const void* src, int64_t bytes, void* cudaStream) {
+    if (!dst || !src || bytes < 0) return XNART_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)cudaStream) != cudaSuccess) { cudaGetLastError(); return XNART_ERR_CUDA; }
+    return XNART_OK;
+}
+
 // Page-locked host memory for the frame (so the device->host copy needs no staging).
 void* xnart_alloc_host(int64_t bytes) {
     void* p = nullptr;
