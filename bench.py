@@ -256,7 +256,7 @@ def main():
     #   "p2p"   every rank copies its group straight into a receive buffer of rank 0 (CUDA IPC handle from
     #           xnart_ipc_export, device-to-device xnart_copy_async on a copy stream: copy engines, no SMs); a
     #           one-element all-reduce ordered after the copy is the completion signal.
-    gather_mode = os.environ.get("XNART_BENCH_GATHER", "nccl") if world > 1 else "none"
+    gather_mode = os.environ.get("XNART_BENCH_GATHER", "p2p") if world > 1 else "none"   # 8 GPUs: p2p 95.1, nccl 92.1 Grays/s
     gathered = [None, None]
     recv_ptr, remote_ptr = [None, None], [None, None]
     half_bytes = GROUP * H * W * 4
@@ -264,13 +264,27 @@ def main():
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if gather_mode == "p2p":
         box = [None]
-        if rank == 0:
-            recv_ptr = [capi.alloc_device(local_rank, world * half_bytes) for _ in range(2)]
-            box[0] = [capi.ipc_export(local_rank, p) for p in recv_ptr]
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            if rank == 0:
+                recv_ptr = [capi.alloc_device(local_rank, world * half_bytes) for _ in range(2)]
+                box[0] = [capi.ipc_export(local_rank, p) for p in recv_ptr]
+        except Exception as e:
+            print("bench: CUDA IPC export failed (%s)" % e, file=sys.stderr)
+            box[0] = None
         dist.broadcast_object_list(box, src=0)
-        if rank != 0:
-            remote_ptr = [capi.ipc_open(local_rank, h) for h in box[0]]
-    elif gather_mode == "nccl":
+        try:
+            if box[0] is None:
+                raise RuntimeError("no handles")
+            if rank != 0:
+                remote_ptr = [capi.ipc_open(local_rank, h) for h in box[0]]
+        except Exception as e:
+            print("bench: CUDA IPC open failed on rank %d (%s)" % (rank, e), file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:      # every rank falls back together
+            gather_mode = "nccl"
+    if gather_mode == "nccl":
         gathered = [[torch.zeros((GROUP, H, W), dtype=torch.int32, device=dev) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
 
     warm = max(args.warmup, 3)
