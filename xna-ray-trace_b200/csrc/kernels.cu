@@ -1,20 +1,19 @@
-// kernels.cu — the wavefront trace loop of libxnart.so (hand-written CUDA, sm_100a).
+// kernels.cu — the trace loop of libxnart.so for small MeshOctrees (hand-written CUDA, sm_100a): one thread
+// per ray, the whole CastRay per thread.  (Deep octrees: wavefront.cu.)
 //
 // One frame = one launch sequence on one stream, no host round trip in between:
-//   k_level / k_level_coop, level 0      primary rays generated in-kernel (RayTracer.Render,
-//                         RayTracer.cs:410-421), closest hit, shadow rays, shading; reflection and
-//                         refraction rays appended to the next level's queue with warp-aggregated atomics
-//   k_level / k_level_coop, level 1..D   same, rays read from the queue (the RayTracer.CastRay
-//                         recursion, :506-737, turned into one wave per recursion depth)
-//   k_resolve, level D-1..0   bottom-up colour resolve; every level packs to an 8-bit Color exactly
-//                         where the reference's recursion does (RayTracer.cs:584,699,705), level 0
-//                         writes renderTargetData (RayTracer.cs:425)
-// Queue sizes live in device memory (levelCount/levelBase); every kernel is a grid-stride loop
-// over "however many rays the previous level produced".
-//
-// Two schedules of the same work: k_level walks one ray per thread (best when the octrees are a
-// leaf or two deep, e.g. the 14-triangle crate scene); k_level_coop lets the 8 lanes of an octet
-// walk each ray together (trace.cuh: traceMeshOctet), which keeps deep-tree traversal convergent.
+//   k_level, level 0      primary rays generated in-kernel (RayTracer.Render, RayTracer.cs:410-421), closest
+//                         hit, shadow rays, shading; reflection and refraction rays appended to the next
+//                         level's queue with warp-aggregated atomics
+//   k_level, level 1..D   same, rays read from the queue (the RayTracer.CastRay recursion, :506-737, turned
+//                         into one wave per recursion depth)
+//   k_resolve_chain       opaque scenes: one thread folds a pixel's reflection chain bottom-up, or
+//   k_resolve, level D-1..0   level-wise bottom-up colour resolve (binary path trees of transparent scenes);
+//                         every level packs to an 8-bit Color exactly where the reference's recursion does
+//                         (RayTracer.cs:584,699,705), level 0 writes renderTargetData (RayTracer.cs:425)
+//   k_frame               optional: all of the above in one cooperative launch (XNART_OPT_FUSE_FRAME)
+// Queue sizes live in device memory (levelCount/levelBase); every kernel is a grid-stride loop over "however
+// many rays the previous level produced".
 #include <algorithm>
 
 #include "kernels.h"
