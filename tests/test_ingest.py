@@ -1,0 +1,146 @@
+"""Mesh ingest (xna_ray_trace_b200/ingest.py): ASCII FBX 6.1 reader + TracerModelProcessor conventions
+(RayTracePipeline/TracerModelProcessor.cs:133-307).  CPU only.  The shipped models live under /root/reference,
+which does not travel to the GPU box: those tests are skipped when it is absent; the parser and the processor
+conventions are also checked on a hand-written FBX text."""
+import os
+
+import numpy as np
+import pytest
+
+from xna_ray_trace_b200 import ingest, scenes
+
+CONTENT = "/root/reference/RayTraceProject/RayTraceProjectContent"
+needs_reference = pytest.mark.skipif(not os.path.isdir(CONTENT), reason="reference assets not present")
+
+QUAD_FBX = """; FBX 6.1.0 project file
+Objects:  {
+	Model: "Model::Lamp", "Light" {
+		Version: 232
+	}
+	Model: "Model::Quad", "Mesh" {
+		Version: 232
+		Properties60:  {
+			Property: "Lcl Translation", "Lcl Translation", "A+",1.000000,2.000000,3.000000
+			Property: "Lcl Rotation", "Lcl Rotation", "A+",0.0,0.0,0.0
+			Property: "Lcl Scaling", "Lcl Scaling", "A+",2.0,2.0,2.0
+		}
+		Vertices: -1.0,-1.0,0.0,1.0,-1.0,0.0
+		 ,1.0,1.0,0.0,-1.0,1.0,0.0
+		PolygonVertexIndex: 0,1,2,-4
+		LayerElementNormal: 0 {
+			MappingInformationType: "ByPolygon"
+			ReferenceInformationType: "Direct"
+			Normals: 0.0,0.0,1.0
+		}
+		LayerElementUV: 0 {
+			MappingInformationType: "ByPolygonVertex"
+			ReferenceInformationType: "IndexToDirect"
+			UV: 0.0,0.0,1.0,0.0,1.0,1.0,0.0,1.0
+			UVIndex: 0,1,2,3
+		}
+	}
+}
+"""
+
+
+def test_reader_and_processor_on_a_hand_written_quad(tmp_path):
+    p = tmp_path / "quad.fbx"
+    p.write_text(QUAD_FBX)
+    meshes = ingest.read_fbx_meshes(str(p))
+    assert len(meshes) == 1 and meshes[0]["name"] == "Quad"
+    assert meshes[0]["vertices"].shape == (4, 3) and meshes[0]["polygons"] == [[0, 1, 2, 3]]
+    assert meshes[0]["lcl"][0] == (1.0, 2.0, 3.0) and meshes[0]["lcl"][2] == (2.0, 2.0, 2.0)
+    (tris, box), = ingest.process_model(meshes, scale=0.5, diffuse_color=(255, 0, 0, 100))
+    assert len(tris) == 2 and list(tris["id"]) == [0, 1]
+    # absolute transform = Lcl (scale 2, translate (1,2,3)) then the processor's Scale 0.5
+    want = {(-0.5, 0.0, 1.5), (1.5, 0.0, 1.5), (1.5, 2.0, 1.5), (-0.5, 2.0, 1.5)}
+    got = {tuple(np.round(v, 6)) for k in ("v1", "v2", "v3") for v in tris[k]}
+    assert got == want
+    # counter-clockwise FBX polygon with normal +z: triangles are reversed so that Cross(edge2, edge1) = +z
+    assert np.allclose(tris["surfaceNormal"], [[0, 0, 1], [0, 0, 1]], atol=1e-6)
+    assert np.allclose(tris["n1"], [[0, 0, 1], [0, 0, 1]], atol=1e-6)
+    # first triangle (0, 2, 1) after the reversal; v is flipped
+    assert np.allclose(tris["uv1"][0], [0, 1]) and np.allclose(tris["uv2"][0], [1, 0]) and np.allclose(tris["uv3"][0], [1, 1])
+    assert np.allclose(tris["color"][0], [1.0, 0.0, 0.0, np.float32(100) / np.float32(255)])
+    # CreateBoundingBox is seeded with the origin (TracerModelProcessor.cs:246)
+    assert np.allclose(box, [-0.5, 0.0, 0.0, 1.5, 2.0, 1.5])
+    with pytest.raises(ValueError):
+        b = tmp_path / "bin.fbx"
+        b.write_bytes(b"Kaydara FBX Binary  \x00\x1a\x00" + bytes(64))
+        ingest.read_fbx_meshes(str(b))
+
+
+@needs_reference
+@pytest.mark.parametrize("name,n_tris", [("Sphere", 960), ("cube", 12), ("plane", 2), ("prism2", 8), ("torus", 1152), ("monkey", 968)])
+def test_shipped_models_have_the_surveyed_triangle_counts(name, n_tris):
+    """triangles of the traceable assets after fan triangulation."""
+    meshes = ingest.read_fbx_meshes(os.path.join(CONTENT, name + ".fbx"))
+    assert sum(sum(len(p) - 2 for p in m["polygons"]) for m in meshes) == n_tris
+
+
+@needs_reference
+def test_default_sphere_follows_the_processor_conventions(oracle_mod):
+    """Sphere.fbx with the content project's parameters (contentproj:87-96: Scale 2, DiffuseColor 255,0,0,100):
+    482 vertices, 960 triangles of radius 2, outward surface normals, unit vertex normals, origin-seeded box;
+    and the reference's default scene (Game1.cs:98-107) built from it renders like the synthetic stand-in."""
+    raw = ingest.read_fbx_meshes(os.path.join(CONTENT, "Sphere.fbx"))
+    assert len(raw) == 1 and raw[0]["vertices"].shape == (482, 3)
+    (tris, box), = ingest.process_model(raw, scale=2.0, diffuse_color=(255, 0, 0, 100))
+    assert len(tris) == 960
+    for k in ("v1", "v2", "v3"):
+        r = np.linalg.norm(tris[k], axis=1)
+        assert np.all(np.abs(r - 2.0) < 1e-3)
+    centroid = (tris["v1"] + tris["v2"] + tris["v3"]) / 3.0
+    assert np.all(np.einsum("ij,ij->i", tris["surfaceNormal"], centroid) > 0)        # outward
+    for k in ("n1", "n2", "n3"):
+        assert np.all(np.abs(np.linalg.norm(tris[k], axis=1) - 1.0) < 1e-5)
+        assert np.all(np.einsum("ij,ij->i", tris[k], tris["v" + k[1]]) > 1.9)       # normals of a sphere are radial
+    assert np.allclose(box, [-2, -2, -2, 2, 2, 2], atol=1e-3)
+    assert np.allclose(tris["color"][0], [1.0, 0.0, 0.0, np.float32(100) / np.float32(255)])
+    # the Lcl Rotation of -90 degrees about X (Blender's z-up) has been baked: poles on the y axis
+    assert np.abs(tris["v1"][:, 1]).max() > 1.99
+
+    s = scenes.SceneData("default_from_fbx")
+    s.meshes.append(scenes.MeshData(tris, reflectiveness=0.7, transparent=True, refraction_index=1.32, box=box))
+    for x in range(2):
+        for y in range(2):
+            s.objects.append(scenes.ObjectData([0], position=(-7.5 + 5 * x, 2, -7.5 + 5 * y)))
+    ref = scenes.spheres_scene()
+    s.lights, s.camera = ref.lights, ref.camera
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    img = o.render_frame(s.frame(96, 96), n_threads=4)
+    o2 = oracle_mod.Oracle()
+    scenes.upload(o2, ref)
+    img2 = o2.render_frame(ref.frame(96, 96), n_threads=4)
+    cover, cover2 = (img != 0xFF000000), (img2 != 0xFF000000)
+    assert cover.sum() > 100 and abs(int(cover.sum()) - int(cover2.sum())) < 0.1 * cover2.sum()   # same silhouettes
+
+
+@needs_reference
+def test_game1_load_content_from_the_shipped_asset(oracle_mod):
+    """Game1.LoadContent (Game1.cs:74-141) with the real Sphere.fbx through the host mirror: `LoadModel` plays
+    Content.Load<Model>("sphere") with the content project's processor parameters."""
+    import math
+
+    from xna_ray_trace_b200 import host, xna
+
+    meshes = host.LoadModel(os.path.join(CONTENT, "Sphere.fbx"), Scale=2, DiffuseColor=(255, 0, 0, 100), Reflectiveness=0.7,
+                            Transparent=True, RefractionIndex=1.32)
+    assert len(meshes) == 1 and len(meshes[0].Triangles) == 960 and meshes[0].MeshMaterial.InterpolateNormals
+    scene = host.OctreeSpatialManager(backend=oracle_mod.Oracle())
+    for x in range(2):
+        for y in range(2):
+            scene.Bodies.append(host.SceneObject(meshes, (-7.5 + 5 * x, 2, -7.5 + 5 * y), (0, 0, 0)))
+    scene.Build()
+    tracer = host.RayTracer()
+    tracer.CurrentScene = scene
+    tracer.CurrentCamera = host.Camera((0, 16, 32), (0, 0, 0), (0, 1, 0), math.pi / 4, xna.aspect_ratio(80, 80), 1.0, 1000.0)
+    tracer.Viewport = (80, 80)
+    tracer.MaxReflections = 8
+    light = host.SpotLight()
+    light.Color, light.Position, light.Direction = (1, 1, 1), (0, 5, 20), -xna.normalize(xna.v3(0, 5, 20))
+    light.SpotAngle, light.Intensity = math.pi / 2, 1.0
+    tracer.Lights.append(light)
+    img = tracer.Render()
+    assert (img != 0xFF000000).sum() > 100 and ((img & 0xFF) > ((img >> 8) & 0xFF)).sum() > 50   # red spheres

@@ -86,6 +86,19 @@ class Mesh:
             argb=argb, box=self.MeshBoundingBox, item_threshold=self.itemTreshold)
 
 
+def LoadModel(path, Scale=1.0, RotationX=0.0, RotationY=0.0, RotationZ=0.0, DiffuseColor=(0, 0, 0, 0), Reflectiveness=0.0,
+              UseTexture=False, Transparent=False, RefractionIndex=0.0, TextureFilePath=None, InterpolateNormals=True):
+    """`Content.Load<Model>(name).Tag["Meshes"]` for an ASCII FBX 6.1 asset: what FbxImporter + TracerModelProcessor
+    (RayTracePipeline/TracerModelProcessor.cs:105-242) bake at build time, with the processor parameters of
+    RayTraceProjectContent.contentproj as keyword arguments (`ingest.py`; importer conventions unpinned)."""
+    from . import ingest
+
+    mat = Material(Reflectiveness, UseTexture, Transparent, RefractionIndex, TextureFilePath)  # CreateMaterial (:121-131)
+    mat.InterpolateNormals = InterpolateNormals
+    models = ingest.load_model(path, scale=Scale, rotation_deg=(RotationX, RotationY, RotationZ), diffuse_color=DiffuseColor)
+    return [Mesh(tris, mat, box) for tris, box in models]
+
+
 class SceneObject:
     """An instance of a model's meshes (SceneObject.cs).  `meshes` plays the role of Model.Tag["Meshes"]."""
 
