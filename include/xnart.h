@@ -232,6 +232,9 @@ int32_t xnart_debug_tree_info(XnartCtx* ctx, int32_t which, int32_t id, int32_t*
                               int32_t* nRefs, int32_t* nCons, int32_t* depth);
 int32_t xnart_debug_tree_dump(XnartCtx* ctx, int32_t which, int32_t id, float* lo3, float* hi3,
                               int32_t* w0, int32_t* w1, float* consMax3, int32_t* refs);
+/* The 128-byte node expansion records of mesh `id` (32 floats per internal node: 12 child planes, consMax,
+ * 8 child descriptors) and the global bases its record indices / leaf reference positions are relative to. */
+int32_t xnart_debug_inner_dump(XnartCtx* ctx, int32_t id, float* records32, int32_t* innerBase, int32_t* refBase);
 
 #ifdef __cplusplus
 }

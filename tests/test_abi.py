@@ -150,3 +150,40 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in text and "from oracle" not in text, fn
                 assert "libxnart_oracle" not in text and "xnart_oracle" not in text, fn
                 assert "../oracle" not in text and "oracle/" not in text, fn
+
+
+@pytest.mark.parametrize("name", ["grid", "soup", "spheres"])
+def test_expansion_records_describe_the_trees(xnart_lib, name):
+    """The 128-byte node records the persistent kernel expands (device_types.h: 12 child planes, consMax, 8 child
+    descriptors) against the breadth-order trees that are verified node for node against the oracle: every
+    child box is the product of its per-axis halves, bit for bit, and every descriptor names the right leaf
+    run / record.  Host-only context: no GPU needed."""
+    from xna_ray_trace_b200 import scenes
+
+    s = {"grid": lambda: scenes.grid_scene(60), "soup": lambda: scenes.soup_scene(20000, half=14.0), "spheres": scenes.spheres_scene}[name]()
+    x = xnart_lib.Xnart(devices=())
+    scenes.upload(x, s)
+    checked = 0
+    for mid in range(len(s.meshes)):
+        t = x.tree(mid)
+        rec, ib, rb = x.inner_records(mid)
+        inner = np.nonzero(t["w1"] < 0)[0]
+        assert len(rec) == len(inner)
+        for n in inner:
+            k, f = -1 - int(t["w1"][n]), int(t["w0"][n])
+            r = rec[k]
+            desc = r[16:32].view(np.int32).reshape(8, 2)
+            assert np.array_equal(r[12:15], t["cons_max"][k])
+            assert (r[0], r[4], r[8]) == tuple(t["lo"][n])          # the node's own Min is child 0's Min
+            for c in range(8):
+                i, j, kk = c >> 2, (c >> 1) & 1, c & 1
+                lo = (r[0 + 2 * i], r[4 + 2 * j], r[8 + 2 * kk])
+                hi = (r[1 + 2 * i], r[5 + 2 * j], r[9 + 2 * kk])
+                assert lo == tuple(t["lo"][f + c]) and hi == tuple(t["hi"][f + c])
+                if t["w1"][f + c] >= 0:
+                    assert tuple(desc[c]) == (rb + int(t["w0"][f + c]), int(t["w1"][f + c]))
+                else:
+                    assert tuple(desc[c]) == (ib + (-1 - int(t["w1"][f + c])), -1)
+            checked += 1
+    assert checked > (0 if name == "spheres" else 50) or name == "spheres"
+    x.close()

@@ -72,7 +72,7 @@ EXPORTS = [
     "xnart_trace_rays", "xnart_cast_rays", "xnart_render_frames_device",
     "xnart_alloc_device", "xnart_free_device", "xnart_ipc_export", "xnart_ipc_open", "xnart_ipc_close", "xnart_copy_async",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
-    "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump",
+    "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump", "xnart_debug_inner_dump",
 ]
 
 
@@ -246,6 +246,15 @@ class Xnart:
         self._l.xnart_render_frames_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         self._check(self._l.xnart_render_frames_device(self._h, C.cast(arr, C.c_void_p), C.c_int32(n), C.c_void_p(dev_ptr),
                                                        C.c_void_p(stream) if stream else None))
+
+    def inner_records(self, mesh_id=0):
+        """xnart_debug_inner_dump: (records (n_inner, 32) float32, inner base, ref base) of a mesh octree."""
+        n = int((self.tree(mesh_id)["w1"] < 0).sum())
+        rec = np.zeros((max(1, n), 32), dtype=np.float32)[:n]
+        ib, rb = C.c_int32(), C.c_int32()
+        self._l.xnart_debug_inner_dump.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self._l.xnart_debug_inner_dump(self._h, mesh_id, C.c_void_p(rec.ctypes.data) if n else None, C.byref(ib), C.byref(rb)))
+        return rec, ib.value, rb.value
 
     def cast_rays(self, frame, screen_xy):
         """xnart_cast_rays: CastRay through n screen positions (x, y); returns n packed colours."""

@@ -98,6 +98,8 @@ struct XnartCtx {
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
     int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
+    std::vector<float> hostInner;            // expansion records as uploaded (32 floats per internal node)
+    std::vector<int> meshInnerBase, meshRefBase;
     int64_t totalRefs = 0;   // leaf references of all mesh octrees
     std::atomic<int64_t> launches{0};
     XnartCounters last{};
@@ -297,7 +299,6 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
         if (m.tree.depth > kMaxMeshDepth) return fail(c, XNART_ERR_UNSUPPORTED, "mesh octree deeper than the device traversal stack allows");
     }
     if (c->sceneTree.depth > kMaxSceneDepth) return fail(c, XNART_ERR_UNSUPPORTED, "scene octree deeper than the device traversal stack allows");
-    if (c->devs.empty()) { c->built = true; return XNART_OK; }  // host-only context: trees can be exported
 
     // ---- flatten: all mesh trees, then the scene tree, in one node array -------------------------
     size_t nNodes = c->sceneTree.nodeCount(), nCons = c->sceneTree.consMax.size() / 3, nRefs = c->sceneTree.refs.size();
@@ -423,6 +424,17 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     }
     c->nPairs = (int)pairs.size();
     c->totalRefs = (int64_t)nMeshRefs;
+    // kept on the host for xnart_debug_inner_dump (expansion records and per-mesh bases)
+    c->hostInner.assign(reinterpret_cast<const float*>(inner.data()), reinterpret_cast<const float*>(inner.data()) + 4 * inner.size());
+    c->meshInnerBase.clear(); c->meshRefBase.clear();
+    {
+        size_t cb = 0, rb = 0;
+        for (const HostMesh& m : c->meshes) {
+            c->meshInnerBase.push_back((int)cb); c->meshRefBase.push_back((int)rb);
+            cb += m.tree.consMax.size() / 3; rb += m.tree.refs.size();
+        }
+    }
+    if (c->devs.empty()) { c->built = true; return XNART_OK; }  // host-only context: trees and records can be exported
     for (DeviceState& d : c->devs) {
         CU_TRY(c, cudaSetDevice(d.dev));
         CU_TRY(c, cudaStreamSynchronize(d.stream));
@@ -1199,6 +1211,18 @@ int32_t xnart_debug_tree_dump(XnartCtx* c, int32_t which, int32_t id, float* lo3
     std::memcpy(w1, t->w1.data(), t->w1.size() * 4);
     if (consMax3 && !t->consMax.empty()) std::memcpy(consMax3, t->consMax.data(), t->consMax.size() * 4);
     if (refs && !t->refs.empty()) std::memcpy(refs, t->refs.data(), t->refs.size() * 4);
+    return XNART_OK;
+}
+
+// The 128-byte expansion records of mesh `id` as uploaded (32 floats per internal node, device_types.h), plus the
+// global bases that its record indices and leaf reference positions are relative to.  Works in a host-only context.
+int32_t xnart_debug_inner_dump(XnartCtx* c, int32_t id, float* records32, int32_t* innerBase, int32_t* refBase) {
+    if (!c || !c->built || id < 0 || id >= (int)c->meshes.size() || !innerBase || !refBase)
+        return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_debug_inner_dump: bad arguments or scene not built");
+    const size_t n = c->meshes[(size_t)id].tree.consMax.size() / 3;
+    *innerBase = c->meshInnerBase[(size_t)id];
+    *refBase = c->meshRefBase[(size_t)id];
+    if (records32 && n) std::memcpy(records32, c->hostInner.data() + 32 * (size_t)*innerBase, n * 128);
     return XNART_OK;
 }
 
