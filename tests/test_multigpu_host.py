@@ -40,6 +40,12 @@ def _worker(rank, world, port, out_dir):
     f = s.frame(W, H, shard_index=rank, shard_count=world, shard_band_rows=8)
     part = torch.from_numpy(o.render_frame(f).astype(np.int64))
     full = gather_bands(part, H, world, 8, rank, dst=0)
+    # uneven shares (9 bands of 8 rows over 2 ranks: 5 + 4) and a height that is no multiple of the band (row lists)
+    gathered_extra = {}
+    for h2, band in ((72, 8), (70, 8)):
+        f2 = s.frame(W, h2, shard_index=rank, shard_count=world, shard_band_rows=band)
+        p2 = torch.from_numpy(o.render_frame(f2).astype(np.int64))
+        gathered_extra[h2] = gather_bands(p2, h2, world, band, rank, dst=0)
     # (2) a flythrough: frame i belongs to rank i % world
     n_frames = 5
     mine = {}
@@ -50,6 +56,8 @@ def _worker(rank, world, port, out_dir):
     frames = gather_frames(mine, n_frames, (H, W), torch.int64, world, rank, dst=0)
     if rank == 0:
         np.save(os.path.join(out_dir, "full.npy"), full.numpy())
+        for h2, g in gathered_extra.items():
+            np.save(os.path.join(out_dir, "full_%d.npy" % h2), g.numpy())
         np.save(os.path.join(out_dir, "frames.npy"), torch.stack(frames).numpy())
     assert sorted(band_rows(H, rank, world, 8)) == [y for y in range(H) if (y // 8) % world == rank]
     dist.barrier()
@@ -67,6 +75,8 @@ def test_world_size_2_gloo(tmp_path, oracle_mod):
     W, H = 96, 64
     want = o.render_frame(s.frame(W, H)).astype(np.int64)
     assert np.array_equal(np.load(tmp_path / "full.npy"), want)
+    for h2 in (72, 70):
+        assert np.array_equal(np.load(tmp_path / ("full_%d.npy" % h2)), o.render_frame(s.frame(W, h2)).astype(np.int64)), h2
     frames = np.load(tmp_path / "frames.npy")
     for i in range(5):
         cam = scenes.orbit_camera(i, n_frames=5, radius=72.0, height_y=35.0, target=(0.0, 11.8, 0.0))
