@@ -58,5 +58,29 @@ def main():
               "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def make_multisample():
+    """Adaptive multisampling (RayTracer.cs:128-311) and its ray casts: one small frame per quality and a set of
+    sub-pixel sample colours, from the oracle's literal recursion."""
+    out = {}
+    for name, factory in (("crate", scenes.crate_scene), ("grid48", lambda: scenes.grid_scene(48))):
+        s = factory()
+        o = O.Oracle(mode=O.Oracle.MODE_LITERAL, semantics=0)
+        scenes.upload(o, s)
+        f = s.frame(96, 72, max_reflections=2)
+        rng = np.random.default_rng(23)
+        xy = rng.uniform(-1.0, 97.0, size=(3000, 2)).astype(np.float32)
+        xy[:, 1] *= 0.75
+        out[name + "_xy"] = xy
+        out[name + "_samples"] = o.cast_samples(f, xy)
+        for q in (0, 2):
+            out["%s_q%d" % (name, q)] = o.render_frame_multisample(f, q, n_threads=os.cpu_count())
+    np.savez_compressed(os.path.join(HERE, "multisample.npz"), width=96, height=72, max_reflections=2, **out)
+    print("multisample bytes", os.path.getsize(os.path.join(HERE, "multisample.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "multisample":
+        make_multisample()
+    else:
+        main()
+        make_multisample()

@@ -46,3 +46,32 @@ def test_gpu_reproduces_golden(xnart_lib, name):
     scenes.upload(x, s)
     _check(x, _load(name), s)
     x.close()
+
+
+def _check_multisample(api):
+    """multisample.npz: sample colours through the ray-cast entry, and the multisampled frames through the host
+    mirror's level-synchronous refinement on top of that entry."""
+    from xna_ray_trace_b200 import host
+
+    g = _load("multisample")
+    for name in ("crate", "grid48"):
+        s = FACTORY[name]()
+        a = api()
+        scenes.upload(a, s)
+        f = s.frame(int(g["width"]), int(g["height"]), max_reflections=int(g["max_reflections"]))
+        assert np.array_equal(a.cast_rays(f, g[name + "_xy"]), g[name + "_samples"]), name
+        tracer = host.RayTracer()
+        for q in (0, 2):
+            tracer.MultisampleQuality = q
+            got = tracer._render_with_multisampling(a, f, int(g["width"]), int(g["height"]))
+            assert np.array_equal(got, g["%s_q%d" % (name, q)]), (name, q)
+        a.close()
+
+
+def test_oracle_reproduces_multisample_golden(oracle_mod):
+    _check_multisample(oracle_mod.Oracle)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_multisample_golden(xnart_lib):
+    _check_multisample(xnart_lib.Xnart)
