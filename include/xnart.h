@@ -117,8 +117,11 @@ enum {
     XNART_OPT_FUSE_FRAME = 5,    /* 0/1 (default 0): shallow scenes render a frame in one cooperative launch */
     XNART_OPT_OVERLAP_LEVELS = 6, /* 0/1 (default 1): wavefront path runs a level's shadow batch beside the next level */
     XNART_OPT_CHAIN_RESOLVE = 8, /* 0/1 (default 1): opaque scenes fold a pixel's reflection chain in one launch */
-    XNART_OPT_SPLIT_RAYS = 7     /* wavefront path: batches of at most this many rays are traced as 8 segment queries per
+    XNART_OPT_SPLIT_RAYS = 7,    /* wavefront path: batches of at most this many rays are traced as 8 segment queries per
                                     ray, which shortens the serial tail of deep levels (default 131072, 0 = never) */
+    XNART_OPT_PATH_KERNEL = 9    /* 0/1 (default 1): small opaque scenes (single-leaf octrees that fit a kernel parameter,
+                                    e.g. Free_crate) render a frame with ONE persistent launch: a thread follows a pixel's
+                                    whole reflection chain, the scene is read from the constant bank (csrc/path.cu) */
 };
 
 typedef struct XnartCtx XnartCtx;

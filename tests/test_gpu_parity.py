@@ -47,9 +47,10 @@ def assert_hits_identical(a, b):
         assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
 
 
-# kernel schedules (XNART_OPT_TRAVERSAL): 1 = one thread per ray, 2 = wavefront (persistent trace kernel; scenes
-# whose OctreeSpatialManager tree has internal nodes — "many" — fall back to 1)
-SCHEDULES = [1, 2]
+# kernel schedules (XNART_OPT_TRAVERSAL): 0 = automatic (small opaque scenes such as the crate: ONE persistent
+# path-kernel launch per frame, csrc/path.cu), 1 = one thread per ray, 2 = wavefront (persistent trace kernel;
+# scenes whose OctreeSpatialManager tree has internal nodes — "many" — fall back to 1)
+SCHEDULES = [0, 1, 2]
 
 
 @pytest.mark.parametrize("schedule", SCHEDULES)
@@ -458,3 +459,117 @@ def test_edge_cases(X, oracle_mod, schedule):
         f = s.frame(96, 64)
         assert np.array_equal(x.render_frame(f), o.render_frame(f, n_threads=4))
         x.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json sizes against the oracle (every pixel), and the path kernel against the level kernels
+# ---------------------------------------------------------------------------------------------
+def test_path_kernel_is_one_launch_and_equals_level_kernels(X):
+    """Small opaque scenes render a frame with ONE persistent launch (csrc/path.cu).  It executes the same per-ray
+    algorithm as the level kernels, so a 1080p crate frame, its ray counts and the instrumented work counters are
+    identical; sample batches (xnart_cast_rays), shards and odd sizes (scanline pixel order) as well."""
+    s = make_scene("crate")
+    x = X.Xnart()
+    scenes.upload(x, s)
+    f = s.frame(1920, 1080)
+    x.set_option(records.OPT_COUNTERS, 1)
+    n0 = x.kernel_launches()
+    a = x.render_frame(f).copy()
+    assert x.kernel_launches() - n0 == 1
+    ca = x.counters()
+    x.set_option(records.OPT_PATH_KERNEL, 0)
+    n0 = x.kernel_launches()
+    b = x.render_frame(f).copy()
+    assert x.kernel_launches() - n0 > 1
+    cb = x.counters()
+    assert np.array_equal(a, b)
+    for k in ("raysPrimary", "raysShadow", "raysReflection", "raysRefraction", "hits", "pixels", "nBox", "nTriRef", "nTriCulled", "nTriFull"):
+        assert getattr(ca, k) == getattr(cb, k), k
+    x.set_option(records.OPT_COUNTERS, 0)
+    rng = np.random.default_rng(9)
+    xy = rng.uniform(-4.0, 1924.0, size=(50000, 2)).astype(np.float32)
+    xy[:, 1] *= 1080.0 / 1920.0
+    for wh, kw in (((1920, 1080), dict(shard_index=1, shard_count=3, shard_band_rows=8)), ((333, 217), {}), ((64, 4), {}), ((7, 3), {})):
+        fr = s.frame(*wh, **kw)
+        x.set_option(records.OPT_PATH_KERNEL, 0)
+        want = x.render_frame(fr).copy()
+        cw = x.cast_rays(fr, xy[:5000])
+        x.set_option(records.OPT_PATH_KERNEL, 1)
+        assert np.array_equal(want, x.render_frame(fr)), wh
+        assert np.array_equal(cw, x.cast_rays(fr, xy[:5000])), wh
+    assert np.array_equal(a, x.render_frame(f))   # run-to-run determinism of the dynamic pixel-to-lane schedule
+    x.close()
+
+
+@pytest.mark.parametrize("wh", [(640, 480), (1920, 1080)])
+def test_crate_at_baseline_sizes_equals_oracle(X, oracle_mod, wh):
+    """BASELINE.json configs[0] (640x480) and configs[1] (1920x1080, "pixel-diff vs CPU reference"): every pixel of
+    the depth-8 Free_crate frame equals the oracle's, and so do the ray counts."""
+    s = make_scene("crate")
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart()
+    scenes.upload(x, s)
+    f = s.frame(*wh)
+    want = o.render_frame(f, n_threads=16)
+    got = x.render_frame(f)
+    diff = int((want != got).sum())
+    assert diff == 0, "%d of %d pixels differ" % (diff, want.size)
+    oc, xc = o.counters(), x.counters()
+    for k in ("raysPrimary", "raysShadow", "raysReflection", "raysRefraction", "hits", "pixels"):
+        assert getattr(oc, k) == getattr(xc, k), k
+    assert len(np.unique(got)) > 1000
+    x.close()
+
+
+def test_monogame_pack_equals_oracle(X, oracle_mod):
+    """XNART_SEMANTICS_MONOGAME (truncating Color pack, divide-form slab test) against the oracle configured the
+    same way, on the crate (single-leaf trees) and on the grid (deep octree: the slab form decides leaf groups)."""
+    for name, wh in (("crate", (320, 240)), ("grid", (240, 135)), ("spheres", (128, 128))):
+        s = make_scene(name)
+        o = oracle_mod.Oracle(semantics=records.SEMANTICS_MONOGAME)
+        scenes.upload(o, s)
+        x = X.Xnart()
+        scenes.upload(x, s)
+        f = s.frame(*wh, semantics=records.SEMANTICS_MONOGAME)
+        want = o.render_frame(f, n_threads=8)
+        got = x.render_frame(f)
+        assert np.array_equal(want, got), (name, int((want != got).sum()))
+        assert (got != x.render_frame(s.frame(*wh))).any(), name
+        x.close()
+
+
+def test_default_spheres_512_equals_oracle(X, oracle_mod):
+    """The scene the reference ships (Game1.cs:44-45,98-138): 4 transparent spheres, 512x512, depth 8."""
+    s = make_scene("spheres")
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart()
+    scenes.upload(x, s)
+    f = s.frame(512, 512)
+    want = o.render_frame(f, n_threads=16)
+    got = x.render_frame(f)
+    assert np.array_equal(want, got), int((want != got).sum())
+    x.close()
+
+
+def test_grid_1M_1080p_sampled_rows_equal_oracle(X, oracle_mod):
+    """The 1M-triangle octree scene of BASELINE.json at 1920x1080, depth 4, 2 lights: 64 scanlines spread over the
+    frame (8 bands of 8 rows) are rendered by the oracle and must equal the GPU frame's rows."""
+    s = scenes.grid_scene(707)
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart()
+    scenes.upload(x, s)
+    f = s.frame(1920, 1080)
+    got = x.render_frame(f)
+    want = np.zeros_like(got)
+    rows = []
+    for b in range(8):
+        y0 = 40 + b * 130
+        o.render_frame(f, n_threads=16, rows=(y0, y0 + 8), out=want)
+        rows += list(range(y0, y0 + 8))
+    bad = int((want[rows] != got[rows]).sum())
+    assert bad == 0, "%d of %d sampled pixels differ" % (bad, len(rows) * 1920)
+    assert len(np.unique(got[rows])) > 50
+    x.close()

@@ -175,6 +175,37 @@ struct DevArena {
     unsigned int* fetch;        // [2*(maxLevels+2)] work counters of the trace launches
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Small scenes (the Free_crate configs): when the scene octree is a single leaf, every MeshOctree is
+// a single leaf and no material is transparent, the whole intersection data set is a few hundred
+// bytes.  It is then passed to the path kernel (path.cu) BY VALUE as a kernel parameter, i.e. it
+// lives in the constant bank: all lanes of a warp walk the (object, mesh) pairs and their triangles
+// in the same order, so every access is a uniform constant-bank operand — no load instruction, no
+// address arithmetic, no register for the triangle data.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallPairs = 6;    // (object, mesh) pairs in visiting order
+constexpr int kSmallTris = 32;    // leaf references of all distinct meshes together
+struct SmallPair {
+    float inv[12];       // SceneObject.InverseWorld, rows 0..3 x columns 0..2: inv[3*r + c]
+    float world[12];     // SceneObject.World, same packing
+    float box[6];        // Mesh.MeshBoundingBox
+    float rootBox[6];    // MeshOctree root bounds
+    int obj, mesh;
+    int cls;             // transform class (DevObj.xformClass)
+    int first, count;    // run of the mesh's leaf in SmallScene.tri (4 float4 per reference)
+    int refBase;         // global position of the run's first reference in refs[] / leafTri
+    int _pad[2];
+};
+static_assert(sizeof(SmallPair) == 176, "SmallPair layout");
+struct SmallScene {
+    SmallPair pair[kSmallPairs];
+    float4 tri[4 * kSmallTris];   // same 64-byte records as leafTri
+    float sceneBox[6];            // bounds of the scene octree root
+    int nPairs;
+    int _pad;
+};
+
 enum {
     CTR_RAYS_PRIMARY = 0, CTR_RAYS_SHADOW, CTR_RAYS_REFLECTION, CTR_RAYS_REFRACTION, CTR_HITS,
     CTR_NBOX, CTR_NTRIREF, CTR_NTRICULLED, CTR_NTRIFULL, CTR_PIXELS, kCounterSlots = 16

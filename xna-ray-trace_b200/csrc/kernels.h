@@ -32,6 +32,12 @@ cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, 
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
                             int maxBlocks, bool count, cudaStream_t st);
 
+// ---- small opaque scenes (path.cu): the whole frame in one persistent launch -----------------
+int pathKernelBlocksPerSm(bool count);
+// fetch: one zeroed device word (work counter); progress: mapped host word or NULL.
+cudaError_t launchPath(const SmallScene& SS, const DevScene& S, const DevFrame& F, const DevLight* lights, uint32_t* out,
+                       unsigned* fetch, unsigned long long* counters, unsigned* progress, int blocks, bool count, cudaStream_t st);
+
 // ---- wavefront path (wavefront.cu) ----------------------------------------------------------
 int traceKernelBlocksPerSm(bool count);   // resident blocks of the persistent trace kernel
 cudaError_t launchGenPrimary(const DevFrame& F, const DevArena& A, int maxBlocks, cudaStream_t st);

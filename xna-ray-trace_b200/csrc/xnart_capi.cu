@@ -41,6 +41,11 @@ struct DeviceState {
     unsigned long long* stamps = nullptr;   // k_frame: global timer at start / levels done / resolve done
     int frameBlocks = 0, frameBlocksCount = 0;  // resident grid of the cooperative frame kernel
     int traceBlocks = 0, traceBlocksCount = 0;  // resident grid of the persistent trace kernel
+    int pathBlocks = 0, pathBlocksCount = 0;    // resident grid of the persistent path kernel (path.cu)
+    bool lastPath = false;
+    // RayTracer.Progress (RayTracer.cs:43-46): a page-locked word the kernels write through a mapped pointer
+    unsigned* progressHost = nullptr;           // [0] = work units done, as the running kernel last reported
+    unsigned long long progressTotal = 0;       // work units of the render in flight (0 = none)
     int2* pairs = nullptr;
     bool lastWave = false;
     cudaStream_t sideStream = nullptr;                 // shadow batch + shade B of a level (wavefront path)
@@ -98,6 +103,9 @@ struct XnartCtx {
     int traversalMode = 0;   // XNART_OPT_TRAVERSAL: 0 auto, 1 one thread per ray, 2 one octet per ray
     int maxMeshDepth = 0;
     int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
+    SmallScene small{};      // the whole intersection data set as a kernel parameter (path.cu), when it fits
+    bool smallOk = false;
+    bool pathKernel = true;  // XNART_OPT_PATH_KERNEL: small opaque scenes render a frame with one persistent launch
     std::vector<float> hostInner;            // expansion records as uploaded (32 floats per internal node)
     std::vector<int> meshInnerBase, meshRefBase;
     int64_t totalRefs = 0;   // leaf references of all mesh octrees
@@ -185,6 +193,9 @@ int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds)
             cudaDeviceGetAttribute(&coopOk, cudaDevAttrCooperativeLaunch, id);
             if (coopOk) { d.frameBlocks = frameKernelMaxBlocks(false); d.frameBlocksCount = frameKernelMaxBlocks(true); }
             d.traceBlocks = traceKernelBlocksPerSm(false) * d.smCount; d.traceBlocksCount = traceKernelBlocksPerSm(true) * d.smCount;
+            d.pathBlocks = pathKernelBlocksPerSm(false) * d.smCount; d.pathBlocksCount = pathKernelBlocksPerSm(true) * d.smCount;
+            if (cudaHostAlloc(&d.progressHost, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); d.progressHost = nullptr; }
+            if (d.progressHost) std::memset(d.progressHost, 0, 64);
             cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounterSlots);
             c->devs.push_back(d);
         }
@@ -201,6 +212,7 @@ int32_t xnart_destroy(XnartCtx* c) {
         freeScene(d);
         cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.levelWords); cudaFree(d.counters); cudaFree(d.stamps); cudaFree(d.frameBuf);
         if (d.pinned) cudaFreeHost(d.pinned);
+        if (d.progressHost) cudaFreeHost(d.progressHost);
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; k++) { if (d.evRendered[k]) cudaEventDestroy(d.evRendered[k]); if (d.evCopied[k]) cudaEventDestroy(d.evCopied[k]); }
         if (d.copyStream) cudaStreamDestroy(d.copyStream);
@@ -230,6 +242,7 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
         case XNART_OPT_SPLIT_RAYS:
             if (value < 0 || value > (1 << 24)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "split threshold out of range");
             c->splitRays = value; return XNART_OK;
+        case XNART_OPT_PATH_KERNEL: c->pathKernel = value != 0; return XNART_OK;
         case XNART_OPT_TRAVERSAL:
             if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
             c->traversalMode = (int)value; return XNART_OK;
@@ -424,6 +437,41 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     }
     c->nPairs = (int)pairs.size();
     c->totalRefs = (int64_t)nMeshRefs;
+    // Small opaque scene: pairs + leaf records as one kernel parameter (device_types.h: SmallScene, path.cu)
+    c->smallOk = false;
+    if (!pairs.empty() && (int)pairs.size() <= kSmallPairs && c->maxMeshDepth == 0 && !c->hasTransparent) {
+        SmallScene& SS = c->small;
+        std::memset(&SS, 0, sizeof SS);
+        std::vector<int> firstOf(c->meshes.size(), -1);
+        int used = 0;
+        bool fits = true;
+        for (size_t p = 0; p < pairs.size() && fits; p++) {
+            const int oi = pairs[p].x, mi = pairs[p].y;
+            const DevMesh& dm = dmeshes[(size_t)mi];
+            const DevObj& dob = dobjs[(size_t)oi];
+            SmallPair& P = SS.pair[p];
+            if (dm.rootB < 0) { fits = false; break; }   // (cannot happen with maxMeshDepth == 0)
+            if (firstOf[(size_t)mi] < 0) {
+                if (used + dm.rootB > kSmallTris) { fits = false; break; }
+                firstOf[(size_t)mi] = used;
+                std::memcpy(&SS.tri[4 * used], &leafTri[4 * (size_t)dm.rootA], (size_t)dm.rootB * 64);
+                used += dm.rootB;
+            }
+            for (int r = 0; r < 4; r++)
+                for (int col = 0; col < 3; col++) { P.inv[3 * r + col] = dob.inv[4 * r + col]; P.world[3 * r + col] = dob.world[4 * r + col]; }
+            std::memcpy(P.box, dm.box, 24);
+            std::memcpy(P.rootBox, dm.rootBox, 24);
+            P.obj = oi; P.mesh = mi; P.cls = dob.xformClass;
+            P.first = firstOf[(size_t)mi]; P.count = dm.rootB; P.refBase = dm.rootA;
+        }
+        if (fits) {
+            SS.nPairs = (int)pairs.size();
+            const size_t sr = (size_t)sceneRoot;
+            SS.sceneBox[0] = nodes[2 * sr].x; SS.sceneBox[1] = nodes[2 * sr].y; SS.sceneBox[2] = nodes[2 * sr].z;
+            SS.sceneBox[3] = nodes[2 * sr + 1].x; SS.sceneBox[4] = nodes[2 * sr + 1].y; SS.sceneBox[5] = nodes[2 * sr + 1].z;
+            c->smallOk = true;
+        }
+    }
     // kept on the host for xnart_debug_inner_dump (expansion records and per-mesh bases)
     c->hostInner.assign(reinterpret_cast<const float*>(inner.data()), reinterpret_cast<const float*>(inner.data()) + 4 * inner.size());
     c->meshInnerBase.clear(); c->meshRefBase.clear();
@@ -571,6 +619,11 @@ static bool useWave(const XnartCtx* c, const DeviceState& d) {
     return deepScene(c) && c->totalRefs >= 65536;
 }
 
+// One persistent launch per frame (path.cu) for small opaque scenes.
+static bool usePath(const XnartCtx* c, const DeviceState& d) {
+    return c->pathKernel && c->smallOk && c->traversalMode == 0 && !c->fuseFrame && d.pathBlocks > 0 && d.pathBlocksCount > 0;
+}
+
 static int validateFrame(XnartCtx* c, const XnartFrame* f) {
     if (!f) return fail(c, XNART_ERR_INVALID_ARGUMENT, "null frame");
     if (f->vpW <= 0 || f->vpH <= 0) return fail(c, XNART_ERR_INVALID_ARGUMENT, "empty viewport");
@@ -612,6 +665,29 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     const long long localPixels = devSamples ? nSamples : (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
     d.lastPixels = accumulate ? d.lastPixels + localPixels : localPixels;
     d.lastLights = F.nLights;
+    if (usePath(c, d)) {
+        if (localPixels > 0x7fffffffLL) return fail(c, XNART_ERR_UNSUPPORTED, "too many pixels in one shard");
+        // no arena, no chunks: one persistent launch renders the shard (path.cu)
+        F.pixelBase = 0;
+        F.chunkPixels = (int)localPixels;
+        F.tiled = (!devSamples && (f.vpW % 8 == 0) && (localPixels % (4LL * f.vpW) == 0)) ? 1 : 0;
+        d.singleChunk = true; d.lastFused = false; d.lastWave = false; d.lastPath = true;
+        if (!accumulate) {
+            CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
+            CU_TRY(c, cudaEventRecord(d.ev[0], st));
+        }
+        CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * kLevelWords, st));
+        unsigned* fetch = d.levelWords + 3 * (kMaxLevels + 2) + 2;
+        CU_TRY(c, launchPath(c->small, d.scene, F, d.lights, devOut, fetch, d.counters, d.progressHost,
+                             c->countKernels ? d.pathBlocksCount : d.pathBlocks, c->countKernels, st));
+        c->launches++;
+        if (!accumulate) CU_TRY(c, cudaEventRecord(d.ev[1], st));
+        CU_TRY(c, cudaEventRecord(d.ev[2], st));
+        d.lastStream = st;
+        d.countersPending = true;
+        return XNART_OK;
+    }
+    d.lastPath = false;
     // worst-case arena per pixel: a chain of D+1 path nodes, or a full binary tree when a
     // transparent material can fork every hit into reflection + refraction (RayTracer.cs:586-702)
     const double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
@@ -736,7 +812,7 @@ static int collectCounters(XnartCtx* c) {
         unsigned long long h[kCounterSlots];
         unsigned ovf = 0;
         CU_TRY(c, cudaMemcpy(h, d.counters, sizeof h, cudaMemcpyDeviceToHost));
-        CU_TRY(c, cudaMemcpy(&ovf, d.arena.overflow, sizeof ovf, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(&ovf, d.levelWords + 2 * (kMaxLevels + 2), sizeof ovf, cudaMemcpyDeviceToHost));
         if (ovf) return fail(c, XNART_ERR_OUT_OF_MEMORY, "internal: ray queue overflow");
         t.pixels += (uint64_t)d.lastPixels;
         t.raysPrimary += (uint64_t)d.lastPixels;
