@@ -37,6 +37,11 @@ def run(label, opts, inflight=1, n=64):
     return chk
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":   # tuning variants (XNART_LIB=...): the path kernel only
+        tag = os.path.basename(os.environ.get("XNART_LIB", "default"))
+        for k in (1, 2):
+            run(tag, {}, inflight=k)
+        sys.exit(0)
     a = run("path", {})
     b = run("levels", {records.OPT_PATH_KERNEL: 0})
     assert a == b, "frames differ"

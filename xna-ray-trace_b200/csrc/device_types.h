@@ -195,7 +195,8 @@ struct SmallPair {
     int cls;             // transform class (DevObj.xformClass)
     int first, count;    // run of the mesh's leaf in SmallScene.tri (4 float4 per reference)
     int refBase;         // global position of the run's first reference in refs[] / leafTri
-    int _pad[2];
+    int boxCoversRoot;   // 1: rootBox lies inside box component-wise (the Mesh.RayIntersects prefilter cannot reject alone)
+    int _pad;
 };
 static_assert(sizeof(SmallPair) == 176, "SmallPair layout");
 struct SmallScene {

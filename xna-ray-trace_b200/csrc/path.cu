@@ -31,18 +31,22 @@
 #define XN_PATH_THREADS 128
 #endif
 #ifndef XN_PATH_MIN_BLOCKS
-#define XN_PATH_MIN_BLOCKS 5
+#define XN_PATH_MIN_BLOCKS 6
 #endif
 #ifndef XN_PATH_BATCH
 #define XN_PATH_BATCH 64        // pixels a warp takes from the frame per atomic (two 8x4 tiles)
 #endif
+#ifndef XN_PATH_UNROLL
+#define XN_PATH_UNROLL 2       // triangles of the back-face pass in flight per lane
+#endif
 #ifndef XN_PATH_REFILL_MIN
-#define XN_PATH_REFILL_MIN 8    // idle lanes that trigger a refill while other lanes are still on a path
+#define XN_PATH_REFILL_MIN 16   // idle lanes that trigger a refill while other lanes are still on a path
 #endif
 
 namespace xn {
 
 constexpr int kPathLevels = 32;   // >= kMaxLevels + 1 of xnart_capi.cu
+constexpr int kPathUnroll = XN_PATH_UNROLL;
 
 // Vector3.Transform with a matrix packed as 4 rows x 3 columns (SmallPair): m[3*r + c].
 __device__ __forceinline__ V3 transform43p(V3 p, const float* m) {
@@ -65,8 +69,7 @@ __device__ __forceinline__ bool slab6(const float* b, const RayPre& r, float& t)
 //   skip (:290) and IntersectsTriangleBackfaceCulling; `distance < minDistance` keeps the first of equal
 //   distances both inside a mesh (MeshOctree.cs:294) and across meshes / objects
 //   (OctreeSpatialManager.cs:371), which is ONE running strict minimum over the whole visiting order.
-// SHADOW: only the distance is wanted (IsLightPathObstructed compares it with the light's, RayTracer.cs:485).
-template <bool COUNT, bool SHADOW>
+template <bool COUNT>
 __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro, V3 rd, int ignM, int ignT, Hit& out, Ctr& ctr) {
     const unsigned FULL = 0xffffffffu;
     bool live = act && finite3(ro) && finite3(rd);
@@ -98,8 +101,14 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
         }
         bool go = live && rOk;
         float tb, ct;
-        if (COUNT && go) ctr.nBox++;
-        go = slab6(P.box, r, tb) && go;         // Mesh.RayIntersects (Mesh.cs:34-39)
+        // Mesh.RayIntersects (Mesh.cs:34-39).  When the MeshOctree root box lies inside Mesh.MeshBoundingBox
+        // (always, for boxes made by TracerModelProcessor: the mesh box is the vertex box grown to the origin) a ray
+        // that passes the root test passes this one too — every operation of the slab test is monotone in the box
+        // bounds — so the verdict of the pair is the root test's alone; the instrumented build still runs it.
+        if (COUNT || !P.boxCoversRoot) {
+            if (COUNT && go) ctr.nBox++;
+            go = slab6(P.box, r, tb) && go;
+        }
         if (COUNT && go) ctr.nBox++;
         go = slab6(P.rootBox, r, ct) && go;     // root of the MeshOctree (MeshOctree.cs:331)
         if (!__any_sync(FULL, go)) continue;
@@ -112,7 +121,7 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
             const float4* __restrict__ T4 = SS.tri + 4 * (P.first + c0);
             // pass 1: reference identity (:290) and back-face test (RayExtensions.cs:46-51) -> bit mask
             unsigned m = 0u;
-#pragma unroll 4
+#pragma unroll kPathUnroll
             for (int i = 0; i < n; i++) {
                 const float4 nt = T4[4 * i];
                 const bool ig = __float_as_int(nt.w) == ign;
@@ -136,32 +145,53 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
                     const float dist = inv * row1, uu = inv * row2, vv = inv * row3;
                     if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f && dist < bd) {
                         bd = dist;
-                        if (!SHADOW) {
-                            out.u = uu; out.v = vv; out.tri = __float_as_int(nt.w); out.key = P.refBase + c0 + i;
-                            out.obj = P.obj; out.mesh = P.mesh;
-                            // objectSpacePosition = v1 + (v2-v1)*u + (v3-v1)*v (MeshOctree.cs:310-312)
-                            po = add(add(V1, mul(E1, uu)), mul(E2, vv));
-                            improved = true;
-                        }
+                        out.u = uu; out.v = vv; out.tri = __float_as_int(nt.w); out.key = P.refBase + c0 + i;
+                        out.obj = P.obj; out.mesh = P.mesh;
+                        // objectSpacePosition = v1 + (v2-v1)*u + (v3-v1)*v (MeshOctree.cs:310-312)
+                        po = add(add(V1, mul(E1, uu)), mul(E2, vv));
+                        improved = true;
                     }
                 }
             }
         }
-        if (!SHADOW && improved) out.pos = transform43p(po, P.world);   // world = Po * World (:441-443)
+        if (improved) out.pos = transform43p(po, P.world);   // world = Po * World (:441-443)
     }
     out.d = bd;
     return bd < FLT_MAX;
+}
+
+// shard-local pixel index -> (x, y), 32-bit arithmetic (shade.cuh: pixelOf divides 64-bit indices)
+__device__ __forceinline__ void pixelOf32(const DevFrame& F, unsigned q, int& x, int& y) {
+    if (F.samples) { x = (int)q; y = 0; return; }   // sample batch: out[q]
+    unsigned lr;
+    if (F.tiled) {
+        const unsigned rowW = 4u * (unsigned)F.vpW;
+        const unsigned tr = q / rowW;
+        const unsigned within = q - tr * rowW;
+        const unsigned l = within & 31u;
+        x = (int)((within >> 5) * 8u + (l & 7u));
+        lr = tr * 4u + (l >> 3);
+    } else {
+        lr = q / (unsigned)F.vpW;
+        x = (int)(q - lr * (unsigned)F.vpW);
+    }
+    if (F.shardCount > 1) {
+        const unsigned lb = lr / (unsigned)F.shardBandRows, within = lr - lb * (unsigned)F.shardBandRows;
+        y = (int)((lb * (unsigned)F.shardCount + (unsigned)F.shardIndex) * (unsigned)F.shardBandRows + within);
+    } else {
+        y = (int)lr;
+    }
 }
 
 // Level-0 ray of shard-local pixel / sample `idx` (RayTracer.Render, RayTracer.cs:410-421).
 __device__ __forceinline__ void primaryRay(const DevFrame& F, unsigned idx, V3& o, V3& d) {
     float sx, sy;
     if (F.samples) {   // GetColorForQuadrant's sub-pixel positions (RayTracer.cs:220-232)
-        const float2 sp = F.samples[F.pixelBase + idx];
+        const float2 sp = F.samples[idx];
         sx = sp.x; sy = sp.y;
     } else {
         int x, y;
-        pixelOf(F, F.pixelBase + idx, x, y);
+        pixelOf32(F, idx, x, y);
         sx = (float)x; sy = (float)y;
     }
     o = unproject(F, sx, sy, 0.0f);
@@ -169,6 +199,18 @@ __device__ __forceinline__ void primaryRay(const DevFrame& F, unsigned idx, V3& 
     d = normalize(sub(farP, o));
 }
 
+// One lane = one pixel's path; one iteration of the loop = ONE GetRayIntersection query per lane.  A lane is in
+// one of two phases, and lanes of both phases share every query:
+//   q < 0    the closest-hit query of CastRay (:512) for the ray (ro, rd) ignoring triangle (ignM, ignT);
+//            on a hit the lane computes the fragment normal (:520-531) and the reflection direction (:547-550),
+//            and moves ro / ign to the hit: they are the origin / ignore identity both of the shadow rays
+//            (:482-485) and of the reflection ray (:551-559);
+//   q >= 0   IsLightPathObstructed's query towards light q (:465-502); after the last light the surface colour
+//            (:568-581) closes the level: the record goes to the lane's local chain and the reflection ray is the
+//            next query, or — deepest level (:708-727) — the chain is folded and the pixel written.
+// Keeping ONE copy of the query code in the loop matters: the round-1 structure (query, then a second inlined
+// query for the shadow ray) ran at a 73 % instruction-cache hit rate with `no_instruction` the top stall
+// (profiles/r02b_k_path_crate_full.md), and lanes that had missed idled through the shadow query.
 template <bool COUNT>
 __global__ void __launch_bounds__(XN_PATH_THREADS, XN_PATH_MIN_BLOCKS)
 k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant__ DevFrame F, const DevLight* __restrict__ lights,
@@ -187,9 +229,12 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
 
     int pix = -1;       // shard-local pixel this lane is working on, -1 = idle
     int level = 0;      // `iteration` of CastRay
+    int q = -1;         // phase: -1 closest hit, >= 0 shadow query of light q
     // idle lanes carry a harmless ray so that the predicated arithmetic never takes a division slow path
     V3 ro = mk(0.0f, 0.0f, 0.0f), rd = mk(0.48f, 0.6f, 0.64f);
     int ignM = -1, ignT = -1;
+    V3 N = mk(0.0f, 0.0f, 1.0f), lightResult = mk(0.0f, 0.0f, 0.0f);
+    float hu = 0.0f, hv = 0.0f;
     unsigned next = 0u, end = 0u;   // warp-uniform: the batch of pixels this warp is handing out
     bool exhausted = false;         // warp-uniform: the frame has no more batches
 
@@ -219,69 +264,74 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
             }
             if (fresh) {
                 primaryRay(F, (unsigned)pix, ro, rd);
-                level = 0; ignM = -1; ignT = -1;
+                level = 0; q = -1; ignM = -1; ignT = -1;
             }
             if (idle == FULL) break;   // nothing left in the frame and every lane has finished its path
         }
         __syncwarp();
 
-        // ---- CastRay, one recursion depth for every lane that has a ray
+        // ---- one GetRayIntersection query for every lane that has a ray
         const bool act = pix >= 0;
-        Hit h0;
-        const bool hit = traceSmall<COUNT, false>(SS, act, ro, rd, ignM, ignT, h0, ctr);   // :512
-        V3 N = mk(0.0f, 0.0f, 1.0f), lightResult = mk(0.0f, 0.0f, 0.0f);
-        const DevMesh* __restrict__ M = &S.meshes[hit ? h0.mesh : 0];
-        const int triG = hit ? M->triBase + h0.tri : 0;
-        if (hit) N = fragmentNormal(S, M, triG, h0);   // :520-531
-        for (int q = 0; q < F.nLights; q++) {          // :535-542
-            const DevLight& L = lights[q];
-            float distToLight = 0.0f;
-            V3 sd = mk(0.48f, 0.6f, 0.64f);
-            if (hit) sd = shadowDir(L, h0.pos, distToLight);   // IsLightPathObstructed, :467-482
-            Hit sh;
-            const bool shHit = traceSmall<COUNT, true>(SS, hit, h0.pos, sd, h0.mesh, h0.tri, sh, ctr);   // :485
-            if (hit) {
-                // opaque occluders only: amount is 1 or 0 (:487-501); :538-541
-                const float amount = (shHit && sh.d < distToLight) ? 1.0f : 0.0f;
-                if (amount != 1.0f) lightResult = add(lightResult, mul(lightForFragment(L, h0.pos, N), 1.0f - amount));
-            }
-        }
-        if (act) {
-            uint32_t col = 0u;
-            bool done = true;
+        V3 qd = rd;
+        float distToLight = 0.0f;
+        if (act && q >= 0) qd = shadowDir(lights[q], ro, distToLight);   // IsLightPathObstructed, :467-482
+        Hit h;
+        const bool hit = traceSmall<COUNT>(SS, act, ro, qd, ignM, ignT, h, ctr);   // :512 / :485
+        if (!act) continue;
+
+        bool shaded = false, done = false;
+        uint32_t col = 0u;
+        if (q < 0) {
             if (!hit) {
                 col = packColor(mk(0.0f, 0.0f, 0.0f), F.semantics);   // :732
+                done = true;
             } else {
                 nHits++;
-                float alphaW;
-                const V3 surf = surfaceColor(S, F, M, triG, h0.u, h0.v, alphaW);   // :568-581
-                if (!(level < F.maxReflections)) {                                   // :545
-                    col = packColor(mulv(lightResult, surf), F.semantics);           // :726
-                } else {
-                    recA[level] = make_float4(lightResult.x, lightResult.y, lightResult.z, M->oneMinusReflectiveness);
-                    recB[level] = make_float4(surf.x, surf.y, surf.z, 0.0f);
-                    // the reflection ray (:547-559) — always cast, whatever the reflectiveness (Q9)
-                    rd = normalize(reflect(rd, N));
-                    ro = h0.pos; ignM = h0.mesh; ignT = h0.tri;
-                    level++;
-                    nRefl++;
-                    done = false;
-                }
+                const DevMesh* __restrict__ M = &S.meshes[h.mesh];
+                N = fragmentNormal(S, M, M->triBase + h.tri, h);   // :520-531
+                // the reflection ray (:547-559) starts at the hit and ignores its triangle, like the shadow rays
+                rd = normalize(reflect(rd, N));
+                ro = h.pos; ignM = h.mesh; ignT = h.tri;
+                hu = h.u; hv = h.v;
+                lightResult = mk(0.0f, 0.0f, 0.0f);
+                q = 0;
+                shaded = F.nLights == 0;
             }
-            if (done) {
-                // the recursion unwinds: Lerp(reflectionColor.ToVector3(), surfaceColor, 1 - Reflectiveness) * lightResult
-                // (:584) and the 8-bit pack (:705) at every level
-                for (int k = level - 1; k >= 0; k--) {
-                    const float4 a = recA[k], b = recB[k];
-                    const V3 cv = mulv(lerp(unpackColor(col), mk(b.x, b.y, b.z), a.w), mk(a.x, a.y, a.z));
-                    col = packColor(cv, F.semantics);
-                }
-                int x, y;
-                pixelOf(F, F.pixelBase + (long long)pix, x, y);
-                out[(size_t)y * (size_t)F.vpW + (size_t)x] = col;   // renderTargetData[y*W + x] (:425)
-                pix = -1;
-                rd = mk(0.48f, 0.6f, 0.64f);
+        } else {
+            // opaque occluders only: amount is 1 or 0 (:487-501); :538-541
+            const float amount = (hit && h.d < distToLight) ? 1.0f : 0.0f;
+            if (amount != 1.0f) lightResult = add(lightResult, mul(lightForFragment(lights[q], ro, N), 1.0f - amount));
+            q++;
+            shaded = q == F.nLights;
+        }
+        if (shaded) {
+            const DevMesh* __restrict__ M = &S.meshes[ignM];
+            float alphaW;
+            const V3 surf = surfaceColor(S, F, M, M->triBase + ignT, hu, hv, alphaW);   // :568-581
+            if (!(level < F.maxReflections)) {                                           // :545
+                col = packColor(mulv(lightResult, surf), F.semantics);                   // :726
+                done = true;
+            } else {
+                recA[level] = make_float4(lightResult.x, lightResult.y, lightResult.z, M->oneMinusReflectiveness);
+                recB[level] = make_float4(surf.x, surf.y, surf.z, 0.0f);
+                level++;       // the next query is the reflection ray (Q9: cast whatever the reflectiveness)
+                nRefl++;
+                q = -1;
             }
+        }
+        if (done) {
+            // the recursion unwinds: Lerp(reflectionColor.ToVector3(), surfaceColor, 1 - Reflectiveness) * lightResult
+            // (:584) and the 8-bit pack (:705) at every level
+            for (int k = level - 1; k >= 0; k--) {
+                const float4 a = recA[k], b = recB[k];
+                const V3 cv = mulv(lerp(unpackColor(col), mk(b.x, b.y, b.z), a.w), mk(a.x, a.y, a.z));
+                col = packColor(cv, F.semantics);
+            }
+            int x, y;
+            pixelOf32(F, (unsigned)pix, x, y);
+            out[(size_t)y * (size_t)F.vpW + (size_t)x] = col;   // renderTargetData[y*W + x] (:425)
+            pix = -1;
+            ro = mk(0.0f, 0.0f, 0.0f); rd = mk(0.48f, 0.6f, 0.64f);
         }
     }
 

@@ -73,12 +73,15 @@ __device__ __forceinline__ bool slabAxis(float mn, float mx, float p, float inv,
     if (par) {
         if (p < mn || p > mx) return false;
     } else {
-        float t1 = (mn - p) * inv;
-        float t2 = (mx - p) * inv;
-        float tn = (t1 > t2) ? t2 : t1;
-        float tf = (t1 > t2) ? t1 : t2;
-        tmin = maxx(tn, tmin);
-        tmax = minx(tf, tmax);
+        // The framework swaps with `if (t1 > t2)` and accumulates with MathHelper.Max / Min, i.e. compare + select.
+        // For operands that are not NaN that is fminf / fmaxf (one FMNMX each instead of FSETP + FSEL) up to the
+        // sign of a zero, which no later comparison distinguishes.  t1 / t2 cannot be NaN here: the ray is finite
+        // (callers test finite3 first), |d| >= 1e-6 on this branch so inv is finite and non-zero, and the API
+        // rejects NaN coordinates (xnart_add_mesh / xnart_add_object).
+        const float t1 = (mn - p) * inv;
+        const float t2 = (mx - p) * inv;
+        tmin = fmaxf(fminf(t1, t2), tmin);
+        tmax = fminf(fmaxf(t1, t2), tmax);
     }
     return true;
 }

@@ -257,6 +257,17 @@ int32_t xnart_add_mesh(XnartCtx* c, const XnartTriangle* tris, int64_t nTri, con
     if (nTri > 0x7fffffffLL / 8) return fail(c, XNART_ERR_UNSUPPORTED, "xnart_add_mesh: too many triangles");
     if (material->useTexture && (!material->argb || material->texW <= 0 || material->texH <= 0))
         return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_mesh: useTexture without texels");
+    // NaN coordinates are refused: the slab tests on the device use min / max instructions, which equal the
+    // framework's compare-and-select forms only for operands that are not NaN (trace.cuh: slabAxis)
+    for (int a = 0; a < 6; a++) if (box[a] != box[a]) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_mesh: NaN in meshBoxMinMax");
+    {
+        bool nan = false;
+#pragma omp parallel for reduction(|| : nan) if (nTri > 65536)
+        for (long long i = 0; i < (long long)nTri; i++)
+            for (int k = 0; k < 3; k++)
+                if (tris[i].v1[k] != tris[i].v1[k] || tris[i].v2[k] != tris[i].v2[k] || tris[i].v3[k] != tris[i].v3[k]) nan = true;
+        if (nan) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_mesh: NaN vertex coordinate");
+    }
     std::lock_guard<std::mutex> lk(c->renderMutex);
     HostMesh m;
     m.nTri = nTri;
@@ -283,6 +294,9 @@ int32_t xnart_add_object(XnartCtx* c, const int32_t* meshIds, int32_t nMesh, con
                          const float inverseWorld[16], const float localBox[6], int32_t* objIdOut) {
     if (!c || !meshIds || nMesh < 0 || !world || !inverseWorld || !localBox || !objIdOut)
         return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: bad arguments");
+    for (int a = 0; a < 16; a++)
+        if (world[a] != world[a] || inverseWorld[a] != inverseWorld[a]) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: NaN in a matrix");
+    for (int a = 0; a < 6; a++) if (localBox[a] != localBox[a]) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: NaN in localBoxMinMax");
     std::lock_guard<std::mutex> lk(c->renderMutex);
     HostObj o;
     for (int i = 0; i < nMesh; i++) {
@@ -463,6 +477,9 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
             std::memcpy(P.rootBox, dm.rootBox, 24);
             P.obj = oi; P.mesh = mi; P.cls = dob.xformClass;
             P.first = firstOf[(size_t)mi]; P.count = dm.rootB; P.refBase = dm.rootA;
+            P.boxCoversRoot = 1;
+            for (int a = 0; a < 3; a++)
+                if (!(dm.box[a] <= dm.rootBox[a] && dm.box[3 + a] >= dm.rootBox[3 + a])) P.boxCoversRoot = 0;
         }
         if (fits) {
             SS.nPairs = (int)pairs.size();
