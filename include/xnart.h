@@ -119,6 +119,8 @@ enum {
     XNART_OPT_CHAIN_RESOLVE = 8, /* 0/1 (default 1): opaque scenes fold a pixel's reflection chain in one launch */
     XNART_OPT_SPLIT_RAYS = 7,    /* wavefront path: batches of at most this many rays are traced as 8 segment queries per
                                     ray, which shortens the serial tail of deep levels (default 131072, 0 = never) */
+    XNART_OPT_KEEP_COUNTERS = 10, /* 0/1 (default 0): 1 = render calls stop resetting the statistics, xnart_get_counters
+                                    returns totals since the option was set (setting it, to 0 or 1, resets them) */
     XNART_OPT_PATH_KERNEL = 9    /* 0/1 (default 1): small opaque scenes (single-leaf octrees that fit a kernel parameter,
                                     e.g. Free_crate) render a frame with ONE persistent launch: a thread follows a pixel's
                                     whole reflection chain, the scene is read from the constant bank (csrc/path.cu) */
@@ -216,6 +218,18 @@ float xnart_progress(XnartCtx* ctx);
 
 /* Number of CUDA kernels launched by this context so far (for bench.py's gpu_launches). */
 int64_t xnart_kernel_launches(XnartCtx* ctx);
+
+/* VideoStream.AddFrame's bitmap preparation on the device (aviFileWrapper_src/VideoStream.cs:344-365: RotateNoneFlipY +
+ * LockBits as 24bpp): nFrames consecutive width x height Color frames at devRgba8 -> nFrames DIBs at devDib, rows
+ * bottom-up, 3 bytes B,G,R per pixel, every row padded to `stride` bytes (stride >= 3*width).  Enqueued on cudaStream. */
+int32_t xnart_frames_to_dib24(int32_t device, const void* devRgba8, int64_t nFrames, int32_t width, int32_t height,
+                              int32_t stride, void* devDib, void* cudaStream);
+
+/* Measured ceilings of one GPU for the roofline bench.py reports (csrc/microbench.cu; no reference counterpart).
+ * unitsPerSecond: operations/s for XNART_PEAK_FP32_NOFMA (FMUL + FADD without contraction — the arithmetic of this
+ * library), bytes/s for the others; best of `reps` timed launches. */
+enum { XNART_PEAK_FP32_NOFMA = 0, XNART_PEAK_L1_READ = 1, XNART_PEAK_L2_READ = 2, XNART_PEAK_HBM_READ = 3 };
+int32_t xnart_measure_peak(int32_t device, int32_t which, int32_t reps, double* unitsPerSecond);
 
 /* Version / build string (arch, flags). */
 const char* xnart_version(void);

@@ -22,7 +22,7 @@ def built_lib():
 
 def test_exports_match_header(built_lib):
     hdr = open(os.path.join(ROOT, "include", "xnart.h")).read()
-    declared = sorted(set(re.findall(r"\b(xnart_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(xnart_[a-z0-9_]+)\s*\(", hdr)))
     assert declared == sorted(capi.EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), name

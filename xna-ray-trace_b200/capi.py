@@ -72,7 +72,7 @@ EXPORTS = [
     "xnart_trace_rays", "xnart_cast_rays", "xnart_render_frames_device",
     "xnart_alloc_device", "xnart_free_device", "xnart_ipc_export", "xnart_ipc_open", "xnart_ipc_close", "xnart_copy_async",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
-    "xnart_free_host", "xnart_debug_tree_info", "xnart_debug_tree_dump", "xnart_debug_inner_dump",
+    "xnart_free_host", "xnart_measure_peak", "xnart_frames_to_dib24", "xnart_debug_tree_info", "xnart_debug_tree_dump", "xnart_debug_inner_dump",
 ]
 
 
@@ -306,6 +306,30 @@ class Xnart:
         out["refs"] = out["refs"][: nr.value]
         out["cons_max"] = out["cons_max"][: nc.value]
         return out
+
+
+def frames_to_dib24(device, src_ptr, n_frames, width, height, stride, dst_ptr, stream=None):
+    """xnart_frames_to_dib24: n Color frames on the device -> n bottom-up 24bpp DIBs on the device (VideoStream.AddFrame)."""
+    L = lib()
+    L.xnart_frames_to_dib24.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    rc = L.xnart_frames_to_dib24(device, C.c_void_p(src_ptr), n_frames, width, height, stride, C.c_void_p(dst_ptr),
+                                 C.c_void_p(stream) if stream else None)
+    if rc != 0:
+        raise XnartError(rc, "xnart_frames_to_dib24 failed")
+
+
+PEAK_FP32_NOFMA, PEAK_L1_READ, PEAK_L2_READ, PEAK_HBM_READ = 0, 1, 2, 3
+
+
+def measure_peak(device, which, reps=5):
+    """xnart_measure_peak: operations/s (PEAK_FP32_NOFMA) or bytes/s of one GPU, best of `reps` launches."""
+    L = lib()
+    out = C.c_double(0.0)
+    L.xnart_measure_peak.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    rc = L.xnart_measure_peak(device, which, reps, C.byref(out))
+    if rc != 0:
+        raise XnartError(rc, "xnart_measure_peak failed")
+    return out.value
 
 
 def version():

@@ -34,13 +34,13 @@
 #define XN_PATH_MIN_BLOCKS 6
 #endif
 #ifndef XN_PATH_BATCH
-#define XN_PATH_BATCH 64        // pixels a warp takes from the frame per atomic (two 8x4 tiles)
+#define XN_PATH_BATCH 32        // pixels a warp takes from the frame per atomic (one 8x4 tile)
 #endif
 #ifndef XN_PATH_UNROLL
 #define XN_PATH_UNROLL 2       // triangles of the back-face pass in flight per lane
 #endif
 #ifndef XN_PATH_REFILL_MIN
-#define XN_PATH_REFILL_MIN 16   // idle lanes that trigger a refill while other lanes are still on a path
+#define XN_PATH_REFILL_MIN 24   // idle lanes that trigger a refill while other lanes are still on a path
 #endif
 
 namespace xn {

@@ -105,6 +105,7 @@ struct XnartCtx {
     int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
     SmallScene small{};      // the whole intersection data set as a kernel parameter (path.cu), when it fits
     bool smallOk = false;
+    bool keepCounters = false;  // XNART_OPT_KEEP_COUNTERS: statistics accumulate over render calls
     bool pathKernel = true;  // XNART_OPT_PATH_KERNEL: small opaque scenes render a frame with one persistent launch
     std::vector<float> hostInner;            // expansion records as uploaded (32 floats per internal node)
     std::vector<int> meshInnerBase, meshRefBase;
@@ -243,6 +244,19 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
             if (value < 0 || value > (1 << 24)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "split threshold out of range");
             c->splitRays = value; return XNART_OK;
         case XNART_OPT_PATH_KERNEL: c->pathKernel = value != 0; return XNART_OK;
+        case XNART_OPT_KEEP_COUNTERS: {
+            std::lock_guard<std::mutex> lk(c->renderMutex);
+            c->keepCounters = value != 0;
+            for (DeviceState& d : c->devs) {
+                if (cudaSetDevice(d.dev) != cudaSuccess) continue;
+                cudaStreamSynchronize(d.stream);
+                if (d.lastStream) cudaStreamSynchronize(d.lastStream);
+                cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounterSlots);
+                d.lastPixels = 0; d.countersPending = false;
+            }
+            c->last = XnartCounters{};
+            return XNART_OK;
+        }
         case XNART_OPT_TRAVERSAL:
             if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
             c->traversalMode = (int)value; return XNART_OK;
@@ -660,6 +674,8 @@ static int validateFrame(XnartCtx* c, const XnartFrame* f) {
 // Enqueue the whole trace loop of one frame shard on `st`, writing full-frame-indexed RGBA8 to devOut.
 static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st, bool accumulate = false,
                         const float2* devSamples = nullptr, long long nSamples = 0) {
+    const bool timeIt = !accumulate;          // a single render: per-stage events
+    accumulate = accumulate || c->keepCounters;
     DevFrame F;
     {
         // Viewport.Unproject: Invert(Multiply(Multiply(world = Identity, view), proj)) — once per frame
@@ -689,16 +705,14 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         F.chunkPixels = (int)localPixels;
         F.tiled = (!devSamples && (f.vpW % 8 == 0) && (localPixels % (4LL * f.vpW) == 0)) ? 1 : 0;
         d.singleChunk = true; d.lastFused = false; d.lastWave = false; d.lastPath = true;
-        if (!accumulate) {
-            CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
-            CU_TRY(c, cudaEventRecord(d.ev[0], st));
-        }
+        if (!accumulate) CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
+        if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[0], st));
         CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * kLevelWords, st));
         unsigned* fetch = d.levelWords + 3 * (kMaxLevels + 2) + 2;
         CU_TRY(c, launchPath(c->small, d.scene, F, d.lights, devOut, fetch, d.counters, d.progressHost,
                              c->countKernels ? d.pathBlocksCount : d.pathBlocks, c->countKernels, st));
         c->launches++;
-        if (!accumulate) CU_TRY(c, cudaEventRecord(d.ev[1], st));
+        if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[1], st));
         CU_TRY(c, cudaEventRecord(d.ev[2], st));
         d.lastStream = st;
         d.countersPending = true;
@@ -736,10 +750,8 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     d.lastFused = fused;
     d.lastWave = wave;
 
-    if (!accumulate) {
-        CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
-        CU_TRY(c, cudaEventRecord(d.ev[0], st));
-    }
+    if (!accumulate) CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
+    if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[0], st));
     for (long long p0 = 0; p0 < localPixels; p0 += chunk) {
         F.pixelBase = p0;
         F.chunkPixels = (int)std::min(chunk, localPixels - p0);
@@ -822,10 +834,10 @@ static int collectCounters(XnartCtx* c) {
     XnartCounters t{};
     bool any = false;
     for (DeviceState& d : c->devs) {
-        if (!d.countersPending) continue;
+        if (!d.countersPending && !c->keepCounters) continue;
         any = true;
         CU_TRY(c, cudaSetDevice(d.dev));
-        CU_TRY(c, cudaStreamSynchronize(d.lastStream));
+        if (d.lastStream) CU_TRY(c, cudaStreamSynchronize(d.lastStream));
         unsigned long long h[kCounterSlots];
         unsigned ovf = 0;
         CU_TRY(c, cudaMemcpy(h, d.counters, sizeof h, cudaMemcpyDeviceToHost));
@@ -1015,8 +1027,10 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
             CU_TRY(c, cudaMallocHost(&d.pinned, 2 * pixels * 4));
             d.pinnedPixels = 2 * pixels;
         }
-        d.lastPixels = 0;
-        CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+        if (!c->keepCounters) {
+            d.lastPixels = 0;
+            CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+        }
         CU_TRY(c, cudaEventRecord(d.ev[0], d.stream));
     }
     std::vector<int> perDev(nDev, 0);
@@ -1104,8 +1118,10 @@ int32_t xnart_render_frames_device(XnartCtx* c, const XnartFrame* frames, int32_
     for (int si : states) {
         DeviceState& d = c->devs[si];
         if (d.stream != user) CU_TRY(c, cudaStreamWaitEvent(d.stream, d0.evRendered[0], 0));
-        d.lastPixels = 0;
-        CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+        if (!c->keepCounters) {
+            d.lastPixels = 0;
+            CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
+        }
         CU_TRY(c, cudaEventRecord(d.ev[0], d.stream));
     }
     for (int f = 0; f < n; f++) {

@@ -28,29 +28,40 @@ def orbit_cameras(n_frames, radius=90.0, height_y=30.0, target=(0.0, 0.0, 0.0)):
 
 def dib_bits_on_device(frames, bpp, stride):
     """(..., H, W) int32 frames in the XNA Color layout on the device -> (..., H * stride) uint8 DIB bits
-    (rows bottom-up, BGR(A), rows padded to `stride`): VideoStream.AddFrame's RotateNoneFlipY + LockBits, done
-    with three torch ops on the GPU instead of numpy on the host."""
+    (rows bottom-up, BGR, rows padded to `stride`): VideoStream.AddFrame's RotateNoneFlipY + LockBits (VideoStream.cs:
+    345-351), done by libxnart's xnart_frames_to_dib24 kernel on the GPU (24 bpp only)."""
     import torch
 
-    nb = bpp // 8
+    from . import capi
+
+    assert bpp == 24, "the device conversion writes 24bpp DIBs"
     h, w = frames.shape[-2], frames.shape[-1]
-    px = frames.contiguous().view(torch.uint8).reshape(*frames.shape[:-2], h, w, 4)
-    idx = torch.tensor([2, 1, 0, 3][:nb], device=frames.device)
-    bgr = px.index_select(-1, idx).flip(-3).reshape(*frames.shape[:-2], h, w * nb)
-    if stride != w * nb:
-        bgr = torch.nn.functional.pad(bgr, (0, stride - w * nb))
-    return bgr.reshape(*frames.shape[:-2], h * stride)
+    src = frames.contiguous()
+    n = src.numel() // (h * w)
+    out = torch.empty(tuple(frames.shape[:-2]) + (h * stride,), dtype=torch.uint8, device=frames.device)
+    capi.frames_to_dib24(frames.device.index or 0, src.data_ptr(), n, w, h, stride, out.data_ptr(),
+                         torch.cuda.current_stream(frames.device).cuda_stream)
+    return out
 
 
-def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank=0, batch=8, device=None):
+def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank=0, batch=8, device=None, dib24=None):
     """Render `cameras` (one frame each) on this rank's share and deliver the frames in order to `sink`
-    (an avi.VideoStream, or any object with AddFrame) on rank 0.  Returns (frames rendered here, rays
-    traced here, seconds spent here).
+    (an avi.VideoStream, or any object with AddFrame / AddFrameBits) on rank 0.  Returns (frames rendered here,
+    rays traced here — exact, from the device counters —, seconds until the last frame was delivered).
+    dib24: ship 24bpp DIB rows instead of Color frames; every rank must pass the same value (default: rank 0's
+    sink decides when world == 1, False otherwise).
 
-    Frames stay on the device: every rank renders `batch` rounds into one half of a ring, ONE async
-    collective (on NCCL's stream) ships the group to rank 0 while the next group is being rendered, and
-    rank 0 converts a gathered group to DIB bits on the GPU and brings it to the host only to feed the sink."""
+    Frames stay on the device: every rank renders `batch` rounds into one half of a ring and, for a sink that takes
+    raw DIB bits, converts them to 24bpp bottom-up rows there (xnart_frames_to_dib24: 3 bytes per pixel cross NVLink
+    and PCIe instead of 4); ONE async collective (on NCCL's stream) ships the group to rank 0 while the next group
+    is being rendered; rank 0 copies a gathered group into page-locked memory and a writer thread appends it to the
+    sink while rendering goes on."""
+    import queue
+    import threading
+
     import torch
+
+    from . import records
 
     n = len(cameras)
     mine = [f for f in range(n) if frame_owner(f, world) == rank]
@@ -61,34 +72,72 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
         import torch.distributed as dist
     stream = torch.cuda.current_stream()
     rounds = (n + world - 1) // world
+    if dib24 is None:
+        dib24 = world == 1 and sink is not None and hasattr(sink, "AddFrameBits") and getattr(sink, "CountBitsPerPixel", 0) == 24
+    raw = bool(dib24)
     ring = torch.zeros((2, batch, height, width), dtype=torch.int32, device=device)
+    if raw:
+        stride = (width * 3 + 3) & ~3
+        assert sink is None or sink._stride == stride
+        unit_shape, unit_dtype = (batch, height * stride), torch.uint8
+    else:
+        unit_shape, unit_dtype = (batch, height, width), torch.int32
+    ship = [torch.zeros(unit_shape, dtype=unit_dtype, device=device) for _ in range(2)] if raw else [ring[0], ring[1]]
     if world > 1 and rank == 0:
-        recv = [[torch.zeros((batch, height, width), dtype=torch.int32, device=device) for _ in range(world)] for _ in range(2)]
+        recv = [[torch.zeros(unit_shape, dtype=unit_dtype, device=device) for _ in range(world)] for _ in range(2)]
     else:
         recv = [None, None]
     pending = [None, None]   # (work or None, first round, rounds in the group)
-    raw = sink is not None and hasattr(sink, "AddFrameBits")
+
+    # rank 0: page-locked staging buffers and the writer thread
+    writer = None
+    if rank == 0 and sink is not None:
+        free_q, work_q = queue.Queue(), queue.Queue()
+        for _ in range(3):
+            free_q.put(torch.empty((world,) + unit_shape, dtype=unit_dtype, pin_memory=True))
+        failure = []
+
+        def write_loop():
+            while True:
+                item = work_q.get()
+                if item is None:
+                    return
+                buf, ev, r0, cnt = item
+                try:
+                    ev.synchronize()
+                    host = buf.numpy()
+                    for k in range(cnt):
+                        for q in range(world):
+                            if (r0 + k) * world + q < n and not failure:
+                                if raw:
+                                    sink.AddFrameBits(host[q, k])
+                                else:
+                                    sink.AddFrame(host[q, k].view(np.uint32))
+                except Exception as e:   # e.g. disk full: keep draining so the render loop never blocks
+                    failure.append(e)
+                free_q.put(buf)
+
+        writer = threading.Thread(target=write_loop, daemon=True)
+        writer.start()
 
     def deliver(half):
         work, r0, cnt = pending[half]
         if work is not None:
             work.wait()
         pending[half] = None
-        if rank != 0 or sink is None:
+        if writer is None:
             return
-        grp = torch.stack(recv[half]) if world > 1 else ring[half].unsqueeze(0)      # (world, batch, H, W)
-        if raw:
-            host = dib_bits_on_device(grp[:, :cnt], sink.CountBitsPerPixel, sink._stride).cpu().numpy()
-        else:
-            host = grp[:, :cnt].cpu().numpy().view(np.uint32)
-        for k in range(cnt):
+        buf = free_q.get()
+        if world > 1:
             for q in range(world):
-                if (r0 + k) * world + q < n:
-                    if raw:
-                        sink.AddFrameBits(host[q, k].tobytes())
-                    else:
-                        sink.AddFrame(host[q, k])
+                buf[q].copy_(recv[half][q], non_blocking=True)
+        else:
+            buf[0].copy_(ship[half], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        work_q.put((buf, ev, r0, cnt))
 
+    x.set_option(records.OPT_KEEP_COUNTERS, 1)   # exact ray totals over all batches of this rank
     t0 = time.perf_counter()
     for g0 in range(0, rounds, batch):
         half = (g0 // batch) & 1
@@ -99,15 +148,23 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
         fl = [f for f in fl if f < n]      # a rank's frames of a group are consecutive slots 0..len-1
         if fl:
             x.render_frames_device([scene.frame(width, height, camera=cameras[f]) for f in fl], ring[half].data_ptr(), stream.cuda_stream)
-        work = dist.gather(ring[half], recv[half], dst=0, async_op=True) if world > 1 else None
+            if raw:
+                from . import capi
+
+                capi.frames_to_dib24(device.index or 0, ring[half].data_ptr(), len(fl), width, height, stride,
+                                     ship[half].data_ptr(), stream.cuda_stream)
+        work = dist.gather(ship[half], recv[half], dst=0, async_op=True) if world > 1 else None
         pending[half] = (work, g0, cnt)
     for h in sorted([h for h in range(2) if pending[h] is not None], key=lambda h: pending[h][1]):
         deliver(h)
     torch.cuda.synchronize()
+    if writer is not None:
+        work_q.put(None)
+        writer.join()
+        if failure:
+            x.set_option(records.OPT_KEEP_COUNTERS, 0)
+            raise failure[0]
     secs = time.perf_counter() - t0
-    # rays of this rank: the device counters are per render; sample the middle frame of this rank's share
-    rays = 0
-    if mine:
-        x.render_frame_device(scene.frame(width, height, camera=cameras[mine[len(mine) // 2]]), ring[0, 0].data_ptr(), None)
-        rays = x.counters().rays * len(mine)
+    rays = x.counters().rays
+    x.set_option(records.OPT_KEEP_COUNTERS, 0)
     return len(mine), rays, secs
