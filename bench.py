@@ -260,10 +260,15 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        # torchrun pins every rank to ONE OpenMP thread; the native octree builder (csrc/scene_build.cpp) is OpenMP
+        # code and every rank builds its own copy of the scene: give each rank its share of the host cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -668,7 +673,16 @@ def flythrough_avi(x, scene, n_frames, world, rank, dev, torch, dist):
     path, mgr, sink, err = None, None, None, None
     if rank == 0:
         try:
-            fd, path = tempfile.mkstemp(suffix=".avi", prefix="xnart_fly_", dir=os.environ.get("XNART_BENCH_TMP") or None)
+            tmpdir = os.environ.get("XNART_BENCH_TMP")
+            if not tmpdir:
+                # 3.7 GB of frames: a RAM-backed directory when there is one with room, else the system temp directory
+                try:
+                    st = os.statvfs("/dev/shm")
+                    if st.f_bavail * st.f_frsize > (6 << 30):
+                        tmpdir = "/dev/shm"
+                except OSError:
+                    tmpdir = None
+            fd, path = tempfile.mkstemp(suffix=".avi", prefix="xnart_fly_", dir=tmpdir or None)
             os.close(fd)
             mgr = avi.AviManager(path, False)
             sink = mgr.AddVideoStream(False, 30, 0, W, H, avi.PIXELFORMAT_24BPP_RGB)   # 30 fps as Game1.cs:198
@@ -710,6 +724,7 @@ def flythrough_avi(x, scene, n_frames, world, rank, dev, torch, dist):
                         "gathered to rank 0 into an uncompressed 24bpp OpenDML AVI" % (n_frames, scene.max_reflections),
             "n_gpus": world, "scaling": "strong", "frames": n_frames, "seconds": total_s, "frames_per_s": n_frames / total_s,
             "value": rays / total_s / 1e6, "unit": "Mrays/s", "avi_bytes": size, "avi_error": err,
+            "avi_dir": os.path.dirname(path) if path else None, "avi_write_busy_s": getattr(flythrough.render_flythrough, "last_sink_busy_s", None),
             "seconds_until_last_frame_delivered": render_s}
 
 

@@ -84,7 +84,9 @@ typedef struct XnartFrame {
     int32_t maxReflections; /* RayTracer.MaxReflections, RayTracer.cs:33 */
     int32_t filtering;      /* XNART_FILTER_*  */
     int32_t addressMode;    /* XNART_ADDRESS_* */
-    int32_t semantics;      /* XNART_SEMANTICS_* (colour pack + slab test form) */
+    int32_t semantics;      /* XNART_SEMANTICS_*: the Color(Vector3) pack (XNA 4.0 rounds half to even, MonoGame
+                               truncates).  The slab test on the device is always the XNA 4.0 reciprocal-multiply form,
+                               the one the reference links (RayTraceProject.csproj:65); XNART_OPT_SEMANTICS refuses MonoGame */
     /* Row sharding for multi-GPU (RayTracer.cs:49-52 treats scanlines as independent work
      * items): this call renders only scanline bands b with (b % shardCount) == shardIndex,
      * a band being shardBandRows consecutive scanlines.  shardCount <= 1 renders everything. */
@@ -154,6 +156,16 @@ int32_t xnart_add_object(XnartCtx* ctx, const int32_t* meshIds, int32_t nMesh,
                          const float world[16], const float inverseWorld[16],
                          const float localBoxMinMax[6], int32_t* objIdOut);
 
+/* scene.Bodies.Clear(): removes every object (the meshes stay, they are shared by all instances of a model).  A host
+ * mirror calls it at the top of OctreeSpatialManager.Build(), which rebuilds from this.objects on every call
+ * (OctreeSpatialManager.cs:64-99), so that calling Build() twice does not duplicate the scene. */
+int32_t xnart_clear_objects(XnartCtx* ctx);
+
+/* The reference reads SceneObject.World / InverseWorld per ray (OctreeSpatialManager.cs:358-364, 441-443): an object moved
+ * after scene.Build() renders at its new pose, the scene octree keeps the membership it was built with.  Same here: the
+ * matrices are replaced on every device of a built scene without rebuilding the octree. */
+int32_t xnart_set_object_transform(XnartCtx* ctx, int32_t objId, const float world[16], const float inverseWorld[16]);
+
 /* OctreeSpatialManager.Build (OctreeSpatialManager.cs:64-99); itemThreshold = 20.  Flattens
  * and uploads the scene to every device of the context. */
 int32_t xnart_build_scene(XnartCtx* ctx, int32_t itemThreshold);
@@ -213,7 +225,9 @@ int32_t xnart_trace_rays(XnartCtx* ctx, const float* rays6, int64_t n,
 
 int32_t xnart_get_counters(XnartCtx* ctx, XnartCounters* out);
 
-/* RayTracer.Progress (RayTracer.cs:43-46): fraction of the current render that is done. */
+/* RayTracer.Progress (RayTracer.cs:43-46: scanline / Height): fraction of the pixels of the blocking render call in
+ * flight that are finished, reported by the kernels themselves (per pixel batch on small scenes, per recursion level and
+ * arena chunk otherwise); 0 before the first render, 1 after a finished one.  Callable from any thread. */
 float xnart_progress(XnartCtx* ctx);
 
 /* Number of CUDA kernels launched by this context so far (for bench.py's gpu_launches). */

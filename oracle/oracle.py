@@ -87,6 +87,16 @@ class Oracle:
     def set_semantics(self, s):
         self._l.xo_set_semantics(self._h, int(s))
 
+    def set_slab_override(self, s):
+        """-1: the slab test follows XnartFrame.semantics; 0 / 1: XNA 4.0 / MonoGame form whatever the frame says."""
+        self._l.xo_set_slab_override(self._h, int(s))
+
+    def clear_objects(self):
+        self._check(self._l.xo_clear_objects(self._h))
+
+    def set_object_transform(self, obj_id, world, inverse_world):
+        self._check(self._l.xo_set_object_transform(self._h, C.c_int32(obj_id), f32_array(world, 16), f32_array(inverse_world, 16)))
+
     def add_mesh(self, tris, reflectiveness=0.0, use_texture=False, interpolate_normals=False, transparent=False,
                  refraction_index=0.0, argb=None, box=None, item_threshold=50):
         tris = np.ascontiguousarray(tris, dtype=TRIANGLE_DTYPE)

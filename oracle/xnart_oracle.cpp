@@ -742,7 +742,7 @@ using namespace xo;
 
 extern "C" {
 
-struct XoCtx { Ctx c; };
+struct XoCtx { Ctx c; int slabOverride = -1; };
 
 int32_t xo_create(XoCtx** out) { *out = new XoCtx(); return 0; }
 int32_t xo_destroy(XoCtx* h) { delete h; return 0; }
@@ -750,6 +750,9 @@ const char* xo_last_error(XoCtx* h) { return h->c.err.c_str(); }
 // mode: 0 literal (reference algorithm), 1 pruned (order-independent restatement)
 int32_t xo_set_mode(XoCtx* h, int32_t mode) { h->c.mode = mode; return 0; }
 int32_t xo_set_semantics(XoCtx* h, int32_t s) { h->c.semantics = s; return 0; }
+// Slab-test form used while rendering: -1 = follow XnartFrame.semantics (a pure XNA 4.0 or pure MonoGame framework),
+// 0 / 1 = pinned.  libxnart's device code always runs the XNA 4.0 form, whatever colour pack a frame selects.
+int32_t xo_set_slab_override(XoCtx* h, int32_t s) { h->slabOverride = s; return 0; }
 
 static V3 v3(const float* p) { return V3{p[0], p[1], p[2]}; }
 
@@ -801,6 +804,20 @@ int32_t xo_add_object(XoCtx* h, const int32_t* meshIds, int32_t nMesh, const flo
     return 0;
 }
 
+// scene.Bodies.Clear() / a body moved after Build(): the reference reads SceneObject.World / InverseWorld per ray
+// (OctreeSpatialManager.cs:358-364, 441-443) and never rebuilds its tree on its own.
+int32_t xo_clear_objects(XoCtx* h) {
+    h->c.objs.clear();
+    h->c.built = false;
+    return 0;
+}
+int32_t xo_set_object_transform(XoCtx* h, int32_t objId, const float world[16], const float inverseWorld[16]) {
+    if (objId < 0 || objId >= (int)h->c.objs.size()) { h->c.err = "bad object id"; return XNART_ERR_INVALID_ARGUMENT; }
+    h->c.objs[(size_t)objId].world = toM4(world);
+    h->c.objs[(size_t)objId].inv = toM4(inverseWorld);
+    return 0;
+}
+
 int32_t xo_build_scene(XoCtx* h, int32_t itemThreshold) {
     if (!buildSceneTree(h->c, itemThreshold)) { h->c.err = "scene octree exceeds depth guard"; return XNART_ERR_OCTREE_DEPTH; }
     h->c.built = true;
@@ -835,7 +852,7 @@ int32_t xo_render_rows(XoCtx* h, const XnartFrame* f, uint32_t* out, int32_t nTh
     if (f->filtering < 0 || f->filtering > 1 || f->addressMode < 0 || f->addressMode > 2) { c.err = "bad enum"; return XNART_ERR_INVALID_ARGUMENT; }
     resetCounters(c.counters);
     const int savedSem = c.semantics;
-    c.semantics = f->semantics;
+    c.semantics = h->slabOverride >= 0 ? h->slabOverride : f->semantics;
     FrameParams fp{f->maxReflections, f->filtering, f->addressMode, f->semantics};
     const M4 inv = frameInverse(*f);
     std::atomic<int> scanline{y0 - 1};
@@ -921,7 +938,7 @@ int32_t xo_cast_samples(XoCtx* h, const XnartFrame* f, const float* xy, int64_t 
     Ctx& c = h->c;
     if (!c.built) { c.err = "scene not built"; return XNART_ERR_NOT_BUILT; }
     const int savedSem = c.semantics;
-    c.semantics = f->semantics;
+    c.semantics = h->slabOverride >= 0 ? h->slabOverride : f->semantics;
     FrameParams fp{f->maxReflections, f->filtering, f->addressMode, f->semantics};
     const M4 inv = frameInverse(*f);
     LocalCounters lc;
@@ -938,7 +955,7 @@ int32_t xo_render_frame_multisample(XoCtx* h, const XnartFrame* f, int32_t quali
     if (!c.built) { c.err = "scene not built"; return XNART_ERR_NOT_BUILT; }
     resetCounters(c.counters);
     const int savedSem = c.semantics;
-    c.semantics = f->semantics;
+    c.semantics = h->slabOverride >= 0 ? h->slabOverride : f->semantics;
     FrameParams fp{f->maxReflections, f->filtering, f->addressMode, f->semantics};
     const M4 inv = frameInverse(*f);
     std::atomic<int> scanline{-1};

@@ -39,7 +39,27 @@ def golden_rays(frame, n, seed=17):
     return np.concatenate([prim, np.concatenate([org, d], axis=1)]).astype(np.float32)
 
 
+def real_texture_golden():
+    """Free_crate/Diffuse.bmp (the config-1/2 texture) cannot travel to the GPU box; the oracle's frame of the crate
+    scene textured with it is frozen here, where /root/reference exists (tests/test_ingest.py)."""
+    path = "/root/reference/Free_crate/Diffuse.bmp"
+    if not os.path.exists(path):
+        print("skipping the real-texture golden: %s is absent" % path)
+        return
+    from xna_ray_trace_b200 import bmp
+
+    argb = bmp.read_bmp_argb(path)
+    s = scenes.crate_scene(argb=argb)
+    o = O.Oracle(mode=O.Oracle.MODE_LITERAL, semantics=0)
+    scenes.upload(o, s)
+    img = o.render_frame(s.frame(320, 240), n_threads=os.cpu_count())
+    out = os.path.join(HERE, "crate_real_diffuse_320x240.npz")
+    np.savez_compressed(out, frame=img, texture_sum=np.uint64(argb.astype(np.uint64).sum()))
+    print("crate_real_diffuse", img.shape, "bytes", os.path.getsize(out))
+
+
 def main():
+    real_texture_golden()
     for name, (factory, (w, h), nr) in CASES.items():
         s = factory()
         o = O.Oracle(mode=O.Oracle.MODE_LITERAL, semantics=0)

@@ -523,11 +523,13 @@ def test_crate_at_baseline_sizes_equals_oracle(X, oracle_mod, wh):
 
 
 def test_monogame_pack_equals_oracle(X, oracle_mod):
-    """XNART_SEMANTICS_MONOGAME (truncating Color pack, divide-form slab test) against the oracle configured the
-    same way, on the crate (single-leaf trees) and on the grid (deep octree: the slab form decides leaf groups)."""
+    """XnartFrame.semantics selects the Color(Vector3) pack; the slab test on the device is always the XNA 4.0 form
+    (include/xnart.h).  Against the oracle configured the same way — MonoGame's truncating pack, XNA 4.0 slab test —
+    every pixel agrees, on single-leaf trees (crate), a deep octree (grid) and the transparent default scene."""
     for name, wh in (("crate", (320, 240)), ("grid", (240, 135)), ("spheres", (128, 128))):
         s = make_scene(name)
-        o = oracle_mod.Oracle(semantics=records.SEMANTICS_MONOGAME)
+        o = oracle_mod.Oracle()
+        o.set_slab_override(records.SEMANTICS_XNA40)
         scenes.upload(o, s)
         x = X.Xnart()
         scenes.upload(x, s)
@@ -536,6 +538,9 @@ def test_monogame_pack_equals_oracle(X, oracle_mod):
         got = x.render_frame(f)
         assert np.array_equal(want, got), (name, int((want != got).sum()))
         assert (got != x.render_frame(s.frame(*wh))).any(), name
+        with pytest.raises(X.XnartError) as e:     # the MonoGame slab form is not offered on the device
+            x.set_option(records.OPT_SEMANTICS, records.SEMANTICS_MONOGAME)
+        assert e.value.code == records.XNART_ERR_UNSUPPORTED
         x.close()
 
 
@@ -573,3 +578,92 @@ def test_grid_1M_1080p_sampled_rows_equal_oracle(X, oracle_mod):
     assert bad == 0, "%d of %d sampled pixels differ" % (bad, len(rows) * 1920)
     assert len(np.unique(got[rows])) > 50
     x.close()
+
+
+def test_busy_and_progress_under_concurrency(X):
+    """RayTracer.RenderAsync throws while IsBusy (RayTracer.cs:62-63) and Progress is polled from another thread while
+    the render runs (Game1.cs:331-341): a second call issued while a long render holds the context returns
+    XNART_ERR_BUSY, and xnart_progress moves through (0, 1) without ever going backwards."""
+    import threading
+    import time
+
+    s = scenes.grid_scene(707)
+    x = X.Xnart()
+    scenes.upload(x, s)
+    small = s.frame(64, 36)
+    x.render_frame(small)
+    assert x.progress() == 1.0
+    frames = [s.frame(1920, 1080, camera=scenes.CameraData((np.sin(0.2 * i) * 80.0, 40.0, np.cos(0.2 * i) * 80.0), (0.0, 0.0, 0.0)))
+              for i in range(24)]
+    out = np.zeros((len(frames), 1080, 1920), dtype=np.uint32)
+    done = []
+    t = threading.Thread(target=lambda: done.append(x.render_frames(frames, out=out)))
+    t.start()
+    busy, seen = 0, []
+    deadline = time.time() + 60.0
+    while t.is_alive() and time.time() < deadline:
+        seen.append(x.progress())
+        try:
+            x.render_frame(small)
+        except X.BusyError as e:
+            busy += 1
+            assert e.code == records.XNART_ERR_BUSY
+        for bad in (lambda: x.build_scene(), lambda: x.set_object_transform(0, np.eye(4), np.eye(4))):
+            try:
+                bad()
+            except X.XnartError:
+                pass
+        time.sleep(0.002)
+    t.join()
+    assert done and busy > 0
+    mid = [p for p in seen if 0.0 < p < 1.0]
+    assert len(mid) >= 3 and len(set(mid)) >= 3, seen[:20]
+    started = seen.index(mid[0])
+    assert all(b >= a for a, b in zip(seen[started:], seen[started + 1:])), "progress went backwards"
+    assert x.progress() == 1.0
+    # the long call was not disturbed by the rejected ones
+    assert np.array_equal(out[5], x.render_frame(frames[5]))
+    # small scenes report per pixel batch (path kernel): a big crate frame shows intermediate values as well
+    c = make_scene("crate")
+    xc = X.Xnart()
+    scenes.upload(xc, c)
+    big = [c.frame(3840, 2160)] * 40
+    outc = np.zeros((len(big), 2160, 3840), dtype=np.uint32)
+    tc = threading.Thread(target=lambda: xc.render_frames(big, out=outc))
+    tc.start()
+    vals = []
+    while tc.is_alive():
+        vals.append(xc.progress())
+        time.sleep(0.001)
+    tc.join()
+    assert len({v for v in vals if 0.0 < v < 1.0}) >= 3
+    x.close()
+    xc.close()
+
+
+def test_multi_device_context_splits_one_frame(X):
+    """xnart_create with several distinct GPUs: xnart_render_frame deals 8-row bands to the devices, xnart_render_frames
+    whole frames; both give the single-GPU pictures.  Needs two GPUs (skipped on the one-GPU box)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    s = make_scene("crate")
+    x1 = X.Xnart(devices=(0,))
+    scenes.upload(x1, s)
+    x2 = X.Xnart(devices=(0, 1))
+    scenes.upload(x2, s)
+    f = s.frame(640, 480)
+    want = x1.render_frame(f).copy()
+    assert np.array_equal(want, x2.render_frame(f))
+    import math
+    frames = [s.frame(320, 180, camera=scenes.CameraData((math.sin(0.4 * i) * 72.0, 35.0, math.cos(0.4 * i) * 72.0), (0.0, 11.8, 0.0)))
+              for i in range(5)]
+    assert np.array_equal(x1.render_frames(frames), x2.render_frames(frames))
+    g = scenes.grid_scene(120)
+    y1, y2 = X.Xnart(devices=(0,)), X.Xnart(devices=(0, 1))
+    scenes.upload(y1, g); scenes.upload(y2, g)
+    fg = g.frame(320, 200)
+    assert np.array_equal(y1.render_frame(fg), y2.render_frame(fg))
+    for c in (x1, x2, y1, y2):
+        c.close()

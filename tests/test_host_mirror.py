@@ -151,3 +151,52 @@ def test_mirror_on_gpu(xnart_lib, oracle_mod):
     tracer.RenderCompleted.append(lambda s, e: errs.append(e))
     tracer.Render()
     assert isinstance(errs[0], host.ArgumentException)
+
+
+def _rebuild_and_move(backend, oracle_mod):
+    """OctreeSpatialManager.Build() rebuilds from Bodies every time it is called (OctreeSpatialManager.cs:64-99), and
+    SceneObject.World / InverseWorld are read per ray (:358-364): a second Build() must not duplicate the scene, and a
+    body moved after Build() renders at its new pose — inside the octree (and root bounds) it was built with."""
+    size = (80, 80)
+    tracer = load_content(backend, size)
+    first = tracer.Render().copy()
+    scene = tracer.CurrentScene
+    scene.Build()                                   # idempotent: same picture, same amount of work
+    assert np.array_equal(tracer.Render(), first)
+    rays_once = backend.counters().rays
+    scene.Build()
+    tracer.Render()
+    assert backend.counters().rays == rays_once
+    # move one sphere (staying inside the scene's root bounds) without calling Build(): the picture is the one of a
+    # scene built at the new pose
+    scene.Bodies[0].Position = (-7.0, 2.0, -7.0)
+    moved = tracer.Render().copy()
+    assert (moved != first).any()
+    s = scenes.spheres_scene()
+    s.objects[0] = scenes.ObjectData([0], position=(-7.0, 2.0, -7.0))
+    s.finalize()
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    assert np.array_equal(moved, o.render_frame(s.frame(*size), n_threads=4))
+    # a move that leaves the root bounds keeps the stale bounds, as in the reference (the tree is only built by Build())
+    scene.Bodies[1].Position = (-7.5, 5.0, -2.5)
+    stale = tracer.Render().copy()
+    # appending a body takes effect with the next Build()
+    scene.Bodies.append(host.SceneObject(scene.Bodies[0].Meshes, (0.0, 8.0, 0.0), (0, 0, 0)))
+    assert np.array_equal(tracer.Render(), stale)
+    scene.Build()
+    rebuilt = tracer.Render().copy()
+    assert (rebuilt != stale).any()
+    return [first, moved, stale, rebuilt]
+
+
+def test_build_is_idempotent_and_moved_bodies_render_moved(oracle_mod):
+    _rebuild_and_move(oracle_mod.Oracle(), oracle_mod)
+
+
+@pytest.mark.gpu
+def test_build_is_idempotent_and_moved_bodies_render_moved_on_gpu(xnart_lib, oracle_mod):
+    want = _rebuild_and_move(oracle_mod.Oracle(), oracle_mod)
+    got = _rebuild_and_move(xnart_lib.Xnart(), oracle_mod)
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)

@@ -68,7 +68,7 @@ def lib():
 
 EXPORTS = [
     "xnart_create", "xnart_destroy", "xnart_last_error", "xnart_set_option", "xnart_add_mesh", "xnart_add_object",
-    "xnart_build_scene", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_render_frames",
+    "xnart_build_scene", "xnart_clear_objects", "xnart_set_object_transform", "xnart_set_lights", "xnart_render_frame", "xnart_render_frame_device", "xnart_render_frames",
     "xnart_trace_rays", "xnart_cast_rays", "xnart_render_frames_device",
     "xnart_alloc_device", "xnart_free_device", "xnart_ipc_export", "xnart_ipc_open", "xnart_ipc_close", "xnart_copy_async",
     "xnart_get_counters", "xnart_progress", "xnart_kernel_launches", "xnart_version", "xnart_alloc_host",
@@ -208,6 +208,12 @@ class Xnart:
         self._check(self._l.xnart_add_object(self._h, ids, C.c_int32(len(mesh_ids)), f32_array(world, 16),
                                              f32_array(inverse_world, 16), f32_array(local_box, 6), C.byref(out)))
         return out.value
+
+    def clear_objects(self):
+        self._check(self._l.xnart_clear_objects(self._h))
+
+    def set_object_transform(self, obj_id, world, inverse_world):
+        self._check(self._l.xnart_set_object_transform(self._h, C.c_int32(obj_id), f32_array(world, 16), f32_array(inverse_world, 16)))
 
     def build_scene(self, item_threshold=20):
         self._check(self._l.xnart_build_scene(self._h, C.c_int32(item_threshold)))

@@ -141,6 +141,10 @@ struct DevFrame {
     // xnart_cast_rays: primary rays through arbitrary screen positions (x, y) instead of pixel centres;
     // "pixel" q is sample q and its colour goes to out[q]
     const float2* samples;
+    // RayTracer.Progress (RayTracer.cs:43-46): a page-locked host word (mapped) the kernels store "pixels of this call
+    // finished so far on this in-flight state" into; progressBase = pixels of the frames enqueued before this one
+    unsigned long long* progress;
+    unsigned long long progressBase;
 };
 
 // Per-render path arena (SoA over "path nodes": one node per traced primary/reflection/refraction ray).

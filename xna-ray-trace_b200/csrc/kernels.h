@@ -34,9 +34,9 @@ cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, 
 
 // ---- small opaque scenes (path.cu): the whole frame in one persistent launch -----------------
 int pathKernelBlocksPerSm(bool count);
-// fetch: one zeroed device word (work counter); progress: mapped host word or NULL.
+// fetch: one zeroed device word (work counter).
 cudaError_t launchPath(const SmallScene& SS, const DevScene& S, const DevFrame& F, const DevLight* lights, uint32_t* out,
-                       unsigned* fetch, unsigned long long* counters, unsigned* progress, int blocks, bool count, cudaStream_t st);
+                       unsigned* fetch, unsigned long long* counters, int blocks, bool count, cudaStream_t st);
 
 // ---- wavefront path (wavefront.cu) ----------------------------------------------------------
 int traceKernelBlocksPerSm(bool count);   // resident blocks of the persistent trace kernel

@@ -214,8 +214,7 @@ __device__ __forceinline__ void primaryRay(const DevFrame& F, unsigned idx, V3& 
 template <bool COUNT>
 __global__ void __launch_bounds__(XN_PATH_THREADS, XN_PATH_MIN_BLOCKS)
 k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant__ DevFrame F, const DevLight* __restrict__ lights,
-       uint32_t* __restrict__ out, unsigned* __restrict__ fetch, unsigned long long* __restrict__ counters,
-       volatile unsigned* __restrict__ progress) {
+       uint32_t* __restrict__ out, unsigned* __restrict__ fetch, unsigned long long* __restrict__ counters) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned total = (unsigned)F.chunkPixels;
@@ -249,7 +248,8 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
                     if (lane == 0) {
                         b = atomicAdd(fetch, (unsigned)XN_PATH_BATCH);
                         // RayTracer.Progress (RayTracer.cs:43-46): pixels handed out so far, for xnart_progress
-                        if (progress && (b & (64u * XN_PATH_BATCH - 1u)) == 0u) *progress = b < total ? b : total;
+                        if (F.progress && (b & (64u * XN_PATH_BATCH - 1u)) == 0u)
+                            *reinterpret_cast<volatile unsigned long long*>(F.progress) = F.progressBase + (b < total ? b : total);
                     }
                     b = __shfl_sync(FULL, b, 0);
                     if (b >= total) { exhausted = true; break; }
@@ -360,13 +360,13 @@ int pathKernelBlocksPerSm(bool count) {
 }
 
 cudaError_t launchPath(const SmallScene& SS, const DevScene& S, const DevFrame& F, const DevLight* lights, uint32_t* out,
-                       unsigned* fetch, unsigned long long* counters, unsigned* progress, int blocks, bool count, cudaStream_t st) {
+                       unsigned* fetch, unsigned long long* counters, int blocks, bool count, cudaStream_t st) {
     // no more warps than batches: a warp without a batch would only run the exit path
     const long long batches = ((long long)F.chunkPixels + XN_PATH_BATCH - 1) / XN_PATH_BATCH;
     const long long need = (batches + (XN_PATH_THREADS / 32) - 1) / (XN_PATH_THREADS / 32);
     if (need < blocks) blocks = (int)(need < 1 ? 1 : need);
-    if (count) k_path<true><<<blocks, XN_PATH_THREADS, 0, st>>>(SS, S, F, lights, out, fetch, counters, progress);
-    else k_path<false><<<blocks, XN_PATH_THREADS, 0, st>>>(SS, S, F, lights, out, fetch, counters, progress);
+    if (count) k_path<true><<<blocks, XN_PATH_THREADS, 0, st>>>(SS, S, F, lights, out, fetch, counters);
+    else k_path<false><<<blocks, XN_PATH_THREADS, 0, st>>>(SS, S, F, lights, out, fetch, counters);
     return cudaGetLastError();
 }
 

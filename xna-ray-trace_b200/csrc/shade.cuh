@@ -206,6 +206,14 @@ __device__ __forceinline__ void finishHit(const DevScene& S, const DevFrame& F, 
     A.flags[node] = 1u;
 }
 
+// RayTracer.Progress = scanline / Height (RayTracer.cs:43-46).  A frame here is a sequence of recursion levels over a
+// chunk of pixels, not a sweep over scanlines: level L of D+1 (plus the resolve) counts as L/(D+2) of the chunk.
+__device__ __forceinline__ void reportProgress(const DevFrame& F, int level) {
+    if (F.progress)
+        *reinterpret_cast<volatile unsigned long long*>(F.progress) =
+            F.progressBase + (unsigned long long)F.pixelBase + (unsigned long long)F.chunkPixels * (unsigned)level / (unsigned)(F.maxReflections + 2);
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void flushCounters(const DevArena& A, const Ctr& ctr, unsigned nHits, unsigned nRefl, unsigned nRefr) {
     // ray statistics: one atomic per warp and counter
@@ -233,6 +241,7 @@ __device__ __forceinline__ void levelHeader(const DevFrame& F, const DevArena& A
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (level == 0) { A.levelCount[0] = count; A.levelBase[0] = 0u; }
         A.levelBase[level + 1] = base + count;
+        reportProgress(F, level);
     }
 }
 

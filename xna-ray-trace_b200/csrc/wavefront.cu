@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevAren
     const unsigned count = A.levelCount[level];
     const unsigned base = A.levelBase[level];
     const unsigned nextBase = base + count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) A.levelBase[level + 1] = nextBase;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { A.levelBase[level + 1] = nextBase; reportProgress(F, level); }
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
     const int par = level & 1;
     const bool splitL = isSplitBatch(S, A, count);

@@ -6,6 +6,7 @@
 // "host only": it can build and export the flattened octrees (for structural tests) and nothing else.
 #include <atomic>
 #include <cmath>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -44,8 +45,10 @@ struct DeviceState {
     int pathBlocks = 0, pathBlocksCount = 0;    // resident grid of the persistent path kernel (path.cu)
     bool lastPath = false;
     // RayTracer.Progress (RayTracer.cs:43-46): a page-locked word the kernels write through a mapped pointer
-    unsigned* progressHost = nullptr;           // [0] = work units done, as the running kernel last reported
-    unsigned long long progressTotal = 0;       // work units of the render in flight (0 = none)
+    unsigned long long* progressHost = nullptr; // [0] = pixels of the call in flight finished on this state, as the kernels last reported
+    unsigned long long progressEnqueued = 0;    // pixels of the frames enqueued on this state so far in the call in flight
+    // scratch for the batch entry points (xnart_trace_rays / xnart_cast_rays): grows, never shrinks
+    void* scratch = nullptr; size_t scratchBytes = 0;
     int2* pairs = nullptr;
     bool lastWave = false;
     cudaStream_t sideStream = nullptr;                 // shadow batch + shade B of a level (wavefront path)
@@ -88,7 +91,10 @@ struct XnartCtx {
     bool lightsDirty = true;
     bool hasTransparent = false;
     std::mutex renderMutex;
-    std::atomic<float> progress{0.0f};
+    std::atomic<float> progress{0.0f};          // between calls: 0 before the first render, 1 after a finished one
+    std::atomic<bool> rendering{false};         // a blocking render call is in flight: xnart_progress reads the devices' words
+    std::atomic<unsigned long long> progressTotal{0};   // pixels of the call in flight
+    std::vector<DevObj> hostObjs;               // DevObj records as uploaded (xnart_set_object_transform refreshes them)
     std::string err;
     bool countKernels = false;
     int64_t arenaLimit = (int64_t)8 << 30;
@@ -195,7 +201,7 @@ int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds)
             if (coopOk) { d.frameBlocks = frameKernelMaxBlocks(false); d.frameBlocksCount = frameKernelMaxBlocks(true); }
             d.traceBlocks = traceKernelBlocksPerSm(false) * d.smCount; d.traceBlocksCount = traceKernelBlocksPerSm(true) * d.smCount;
             d.pathBlocks = pathKernelBlocksPerSm(false) * d.smCount; d.pathBlocksCount = pathKernelBlocksPerSm(true) * d.smCount;
-            if (cudaHostAlloc(&d.progressHost, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); d.progressHost = nullptr; }
+            if (cudaHostAlloc((void**)&d.progressHost, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); d.progressHost = nullptr; }
             if (d.progressHost) std::memset(d.progressHost, 0, 64);
             cudaMemset(d.counters, 0, sizeof(unsigned long long) * kCounterSlots);
             c->devs.push_back(d);
@@ -214,6 +220,7 @@ int32_t xnart_destroy(XnartCtx* c) {
         cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.levelWords); cudaFree(d.counters); cudaFree(d.stamps); cudaFree(d.frameBuf);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.progressHost) cudaFreeHost(d.progressHost);
+        cudaFree(d.scratch);
         for (auto& ev : d.ev) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; k++) { if (d.evRendered[k]) cudaEventDestroy(d.evRendered[k]); if (d.evCopied[k]) cudaEventDestroy(d.evCopied[k]); }
         if (d.copyStream) cudaStreamDestroy(d.copyStream);
@@ -327,9 +334,62 @@ int32_t xnart_add_object(XnartCtx* c, const int32_t* meshIds, int32_t nMesh, con
     return XNART_OK;
 }
 
+// scene.Bodies.Clear(): the meshes (Model.Tag["Meshes"], shared by all instances) stay, the objects go.  Lets a host
+// mirror make OctreeSpatialManager.Build() idempotent — the reference rebuilds its tree from this.objects on every call
+// (OctreeSpatialManager.cs:64-99) — instead of adding every body a second time.
+int32_t xnart_clear_objects(XnartCtx* c) {
+    if (!c) return XNART_ERR_INVALID_ARGUMENT;
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    c->objs.clear();
+    c->built = false;
+    return XNART_OK;
+}
+
+// The reference reads SceneObject.World / InverseWorld per ray (OctreeSpatialManager.cs:358-364, 441-443), so an object
+// moved after scene.Build() renders at its new pose while the scene octree keeps the leaf membership it was built with.
+// Same here: the matrices of a built scene are replaced on every device, the octree is left alone.
+int32_t xnart_set_object_transform(XnartCtx* c, int32_t objId, const float world[16], const float inverseWorld[16]) {
+    if (!c || !world || !inverseWorld) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_set_object_transform: bad arguments");
+    for (int a = 0; a < 16; a++)
+        if (world[a] != world[a] || inverseWorld[a] != inverseWorld[a]) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_set_object_transform: NaN in a matrix");
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
+    if (objId < 0 || objId >= (int)c->objs.size()) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_set_object_transform: bad object id");
+    HostObj& o = c->objs[(size_t)objId];
+    std::memcpy(o.world, world, 64);
+    std::memcpy(o.inv, inverseWorld, 64);
+    if (!c->built || c->hostObjs.size() != c->objs.size()) return XNART_OK;   // picked up by the next xnart_build_scene
+    std::vector<DevObj>& dobjs = c->hostObjs;
+    for (size_t i = 0; i < c->objs.size(); i++) {
+        DevObj& d = dobjs[i];
+        std::memcpy(d.world, c->objs[i].world, 64);
+        std::memcpy(d.inv, c->objs[i].inv, 64);
+        d.xformClass = (int)i;
+        for (size_t j = 0; j < i; j++)
+            if (std::memcmp(c->objs[j].inv, c->objs[i].inv, 64) == 0) { d.xformClass = dobjs[j].xformClass; break; }
+    }
+    if (c->smallOk)
+        for (int p = 0; p < c->small.nPairs; p++) {
+            SmallPair& P = c->small.pair[p];
+            const DevObj& dob = dobjs[(size_t)P.obj];
+            for (int r = 0; r < 4; r++)
+                for (int col = 0; col < 3; col++) { P.inv[3 * r + col] = dob.inv[4 * r + col]; P.world[3 * r + col] = dob.world[4 * r + col]; }
+            P.cls = dob.xformClass;
+        }
+    for (DeviceState& d : c->devs) {
+        CU_TRY(c, cudaSetDevice(d.dev));
+        CU_TRY(c, cudaStreamSynchronize(d.stream));
+        if (d.lastStream) CU_TRY(c, cudaStreamSynchronize(d.lastStream));
+        CU_TRY(c, cudaMemcpy(d.objs, dobjs.data(), dobjs.size() * sizeof(DevObj), cudaMemcpyHostToDevice));
+    }
+    return XNART_OK;
+}
+
 int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     if (!c || itemThreshold < 0) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_build_scene: bad arguments");
     std::lock_guard<std::mutex> lk(c->renderMutex);
+    c->built = false;   // stays false if anything below fails: a half-uploaded scene must never be rendered
     int rc = buildSceneOctree(c->objs, itemThreshold, c->sceneTree, c->err);
     if (rc != XNART_OK) return rc;
     c->hasTransparent = false;
@@ -465,6 +525,7 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     }
     c->nPairs = (int)pairs.size();
     c->totalRefs = (int64_t)nMeshRefs;
+    c->hostObjs = dobjs;
     // Small opaque scene: pairs + leaf records as one kernel parameter (device_types.h: SmallScene, path.cu)
     c->smallOk = false;
     if (!pairs.empty() && (int)pairs.size() <= kSmallPairs && c->maxMeshDepth == 0 && !c->hasTransparent) {
@@ -694,10 +755,13 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     F.tiled = 0;
     F.samples = devSamples;
     if (devSamples) { F.shardIndex = 0; F.shardCount = 1; F.shardBandRows = 1; }
+    F.progress = c->rendering.load() ? d.progressHost : nullptr;
+    F.progressBase = d.progressEnqueued;
     const int D = f.maxReflections;
     const long long localPixels = devSamples ? nSamples : (long long)localRowsOf(f.vpH, F.shardIndex, F.shardCount, F.shardBandRows) * f.vpW;
     d.lastPixels = accumulate ? d.lastPixels + localPixels : localPixels;
     d.lastLights = F.nLights;
+    d.progressEnqueued += (unsigned long long)localPixels;
     if (usePath(c, d)) {
         if (localPixels > 0x7fffffffLL) return fail(c, XNART_ERR_UNSUPPORTED, "too many pixels in one shard");
         // no arena, no chunks: one persistent launch renders the shard (path.cu)
@@ -709,7 +773,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
         if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[0], st));
         CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * kLevelWords, st));
         unsigned* fetch = d.levelWords + 3 * (kMaxLevels + 2) + 2;
-        CU_TRY(c, launchPath(c->small, d.scene, F, d.lights, devOut, fetch, d.counters, d.progressHost,
+        CU_TRY(c, launchPath(c->small, d.scene, F, d.lights, devOut, fetch, d.counters,
                              c->countKernels ? d.pathBlocksCount : d.pathBlocks, c->countKernels, st));
         c->launches++;
         if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[1], st));
@@ -830,6 +894,26 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     return XNART_OK;
 }
 
+// Brackets of a blocking render call for xnart_progress.
+static void beginProgress(XnartCtx* c, unsigned long long totalPixels) {
+    for (DeviceState& d : c->devs) {
+        if (d.progressHost) *reinterpret_cast<volatile unsigned long long*>(d.progressHost) = 0ULL;
+        d.progressEnqueued = 0;
+    }
+    c->progressTotal = totalPixels;
+    c->progress = 0.0f;
+    c->rendering = true;
+}
+static void endProgress(XnartCtx* c, bool ok) {
+    c->rendering = false;
+    if (ok) c->progress = 1.0f;
+}
+struct ProgressScope {
+    XnartCtx* c; bool ok = false;
+    ProgressScope(XnartCtx* ctx, unsigned long long total) : c(ctx) { beginProgress(c, total); }
+    ~ProgressScope() { endProgress(c, ok); }
+};
+
 static int collectCounters(XnartCtx* c) {
     XnartCounters t{};
     bool any = false;
@@ -883,16 +967,21 @@ int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* de
     DeviceState& d = c->devs[0];
     CU_TRY(c, cudaSetDevice(d.dev));
     cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : d.stream;
-    c->progress = 0.0f;
+    if (cudaStream) {   // asynchronous: the caller owns completion, nothing to poll
+        c->progress = 0.0f;
+        rc = enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
+        if (rc == XNART_OK) c->progress = 1.0f;
+        return rc;
+    }
+    const int sc = frame->shardCount > 1 ? frame->shardCount : 1;
+    ProgressScope ps(c, (unsigned long long)localRowsOf(frame->vpH, sc > 1 ? frame->shardIndex : 0, sc, sc > 1 ? frame->shardBandRows : 1) * (unsigned long long)frame->vpW);
     rc = enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
     if (rc != XNART_OK) return rc;
-    if (!cudaStream) {
-        CU_TRY(c, cudaStreamSynchronize(st));
-        c->last.msCopy = 0; c->last.msTotal = 0;
-        rc = collectCounters(c);
-        c->last.msTotal = c->last.msLevels + c->last.msResolve;
-    }
-    c->progress = 1.0f;
+    CU_TRY(c, cudaStreamSynchronize(st));
+    c->last.msCopy = 0; c->last.msTotal = 0;
+    rc = collectCounters(c);
+    c->last.msTotal = c->last.msLevels + c->last.msResolve;
+    ps.ok = rc == XNART_OK;
     return rc;
 }
 
@@ -905,8 +994,9 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
     int rc = validateFrame(c, frame);
     if (rc != XNART_OK) return rc;
     if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
-    c->progress = 0.0f;
     const size_t pixels = (size_t)frame->vpW * (size_t)frame->vpH;
+    const int psc = frame->shardCount > 1 ? frame->shardCount : 1;
+    ProgressScope ps(c, (unsigned long long)localRowsOf(frame->vpH, psc > 1 ? frame->shardIndex : 0, psc, psc > 1 ? frame->shardBandRows : 1) * (unsigned long long)frame->vpW);
     // One frame is split over DISTINCT GPUs only: a device id listed several times gives several in-flight
     // states for xnart_render_frames (whole frames side by side); splitting one frame over them would only
     // repeat the launch sequence on the same GPU.
@@ -960,7 +1050,6 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
         DeviceState& d = c->devs[prim[i]];
         CU_TRY(c, cudaSetDevice(d.dev));
         CU_TRY(c, cudaStreamSynchronize(d.stream));
-        c->progress = (float)(i + 1) / (float)nDev;
         float a = 0, b = 0;
         cudaEventElapsedTime(&a, d.ev[0], d.ev[3]);
         cudaEventElapsedTime(&b, d.ev[2], d.ev[3]);
@@ -979,7 +1068,7 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
     c->last.msCopy = msCopy; c->last.msTotal = msTotal;
     rc = collectCounters(c);
     c->last.msCopy = msCopy; c->last.msTotal = msTotal;
-    c->progress = 1.0f;
+    ps.ok = rc == XNART_OK;
     return rc;
 }
 
@@ -1001,8 +1090,8 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
             return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames: all frames must share one viewport size and be unsharded");
     }
     if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
-    c->progress = 0.0f;
     const size_t pixels = (size_t)frames[0].vpW * (size_t)frames[0].vpH;
+    ProgressScope ps(c, (unsigned long long)n * (unsigned long long)pixels);
     const int nDev = (int)c->devs.size();
     cudaPointerAttributes pa{};
     const bool outPinned = (cudaPointerGetAttributes(&pa, out) == cudaSuccess) && pa.type == cudaMemoryTypeHost;
@@ -1083,7 +1172,7 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
     c->last.msCopy = 0; c->last.msTotal = msTotal;
     rc = collectCounters(c);
     c->last.msCopy = 0; c->last.msTotal = msTotal;
-    c->progress = 1.0f;
+    ps.ok = rc == XNART_OK;
     return rc;
 }
 
@@ -1107,6 +1196,10 @@ int32_t xnart_render_frames_device(XnartCtx* c, const XnartFrame* frames, int32_
     }
     if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
     const size_t pixels = (size_t)frames[0].vpW * (size_t)frames[0].vpH;
+    // (a NULL stream makes the call blocking: progress can be polled; with a caller's stream nothing is reported)
+    std::unique_ptr<ProgressScope> ps;
+    if (!cudaStream) ps.reset(new ProgressScope(c, (unsigned long long)n * (unsigned long long)pixels));
+    else c->progress = 0.0f;
     std::vector<int> states;   // in-flight states on the GPU of the first entry
     for (int i = 0; i < (int)c->devs.size(); i++)
         if (c->devs[i].dev == c->devs[0].dev) states.push_back(i);
@@ -1141,9 +1234,24 @@ int32_t xnart_render_frames_device(XnartCtx* c, const XnartFrame* frames, int32_
         c->last.msCopy = 0; c->last.msTotal = 0;
         rc = collectCounters(c);
         c->last.msTotal = c->last.msLevels;
+        ps->ok = rc == XNART_OK;
+    } else {
+        c->progress = 1.0f;
     }
-    c->progress = 1.0f;
     return rc;
+}
+
+// Scratch of the batch entry points: one block per in-flight state that only grows (no cudaMalloc / cudaFree per call).
+static cudaError_t ensureScratch(DeviceState& d, size_t bytes) {
+    if (bytes <= d.scratchBytes) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(d.stream);
+    if (e != cudaSuccess) return e;
+    cudaFree(d.scratch);
+    d.scratch = nullptr; d.scratchBytes = 0;
+    bytes += bytes / 4;   // head room: batches of an adaptive-multisampling pass vary in size
+    e = cudaMalloc(&d.scratch, bytes);
+    if (e == cudaSuccess) d.scratchBytes = bytes;
+    return e;
 }
 
 // CastRay for arbitrary screen positions: what GetColorForQuadrant does four times per quadrant
@@ -1163,12 +1271,12 @@ int32_t xnart_cast_rays(XnartCtx* c, const XnartFrame* frame, const float* scree
     if (c->lightsDirty && (rc = uploadLights(c)) != XNART_OK) return rc;
     DeviceState& d = c->devs[0];
     CU_TRY(c, cudaSetDevice(d.dev));
-    float2* ds = nullptr;
-    uint32_t* dout = nullptr;
-    cudaError_t e = cudaMalloc(&ds, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)n * 4);
+    const size_t xyBytes = (((size_t)n * 8) + 255) & ~(size_t)255;
+    cudaError_t e = ensureScratch(d, xyBytes + (size_t)n * 4);
+    float2* ds = (float2*)d.scratch;
+    uint32_t* dout = (uint32_t*)((char*)d.scratch + xyBytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ds, screenXY, (size_t)n * 8, cudaMemcpyHostToDevice, d.stream);
-    if (e != cudaSuccess) { cudaFree(ds); cudaFree(dout); return fail(c, XNART_ERR_CUDA, std::string("xnart_cast_rays: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? XNART_ERR_OUT_OF_MEMORY : XNART_ERR_CUDA, std::string("xnart_cast_rays: ") + cudaGetErrorString(e));
     rc = enqueueFrame(c, d, *frame, dout, d.stream, false, ds, n);
     if (rc == XNART_OK) {
         e = cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, d.stream);
@@ -1177,7 +1285,6 @@ int32_t xnart_cast_rays(XnartCtx* c, const XnartFrame* frame, const float* scree
     } else {
         cudaStreamSynchronize(d.stream);
     }
-    cudaFree(ds); cudaFree(dout);
     if (rc != XNART_OK) return rc;
     c->last.msCopy = 0; c->last.msTotal = 0;
     rc = collectCounters(c);
@@ -1196,22 +1303,30 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
     if (n == 0) return XNART_OK;
     DeviceState& d = c->devs[0];
     CU_TRY(c, cudaSetDevice(d.dev));
-    float *dr = nullptr, *du = nullptr, *dv = nullptr, *dd = nullptr, *dp = nullptr;
-    int *di = nullptr, *dobj = nullptr, *dmesh = nullptr, *dtri = nullptr;
-    float4 *qo = nullptr, *qd = nullptr; int2* qi = nullptr; int4* qh = nullptr; unsigned* qw = nullptr;
     size_t N = (size_t)n;
     if (N > 0x7fffffffULL) return fail(c, XNART_ERR_UNSUPPORTED, "xnart_trace_rays: too many rays in one batch");
-    auto cleanup = [&]() { cudaFree(qo); cudaFree(qd); cudaFree(qi); cudaFree(qh); cudaFree(qw); cudaFree(dr); cudaFree(du); cudaFree(dv); cudaFree(dd); cudaFree(dp); cudaFree(di); cudaFree(dobj); cudaFree(dmesh); cudaFree(dtri); };
-#define TR_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(c, XNART_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(_e)); } } while (0)
-    TR_TRY(cudaMalloc(&dr, N * 24)); TR_TRY(cudaMalloc(&du, N * 4)); TR_TRY(cudaMalloc(&dv, N * 4)); TR_TRY(cudaMalloc(&dd, N * 4));
-    TR_TRY(cudaMalloc(&dp, N * 12)); TR_TRY(cudaMalloc(&dobj, N * 4)); TR_TRY(cudaMalloc(&dmesh, N * 4)); TR_TRY(cudaMalloc(&dtri, N * 4));
-    if (ignore2) { TR_TRY(cudaMalloc(&di, N * 8)); TR_TRY(cudaMemcpyAsync(di, ignore2, N * 8, cudaMemcpyHostToDevice, d.stream)); }
+    const bool wave = useWave(c, d);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t need = al(N * 24) + 6 * al(N * 4) + al(N * 12) + al(N * 8);
+    if (wave) need += 2 * al(N * 16) + al(N * 8) + al(N * 32) + 256;
+    {
+        cudaError_t e = ensureScratch(d, need);
+        if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? XNART_ERR_OUT_OF_MEMORY : XNART_ERR_CUDA, std::string("xnart_trace_rays: ") + cudaGetErrorString(e));
+    }
+    char* sp = (char*)d.scratch;
+    auto take = [&](size_t bytes) { char* r = sp; sp += al(bytes); return r; };
+    float* dr = (float*)take(N * 24);
+    float *du = (float*)take(N * 4), *dv = (float*)take(N * 4), *dd = (float*)take(N * 4), *dp = (float*)take(N * 12);
+    int *dobj = (int*)take(N * 4), *dmesh = (int*)take(N * 4), *dtri = (int*)take(N * 4);
+    int* di = ignore2 ? (int*)take(N * 8) : nullptr;
+    float4 *qo = nullptr, *qd = nullptr; int2* qi = nullptr; int4* qh = nullptr; unsigned* qw = nullptr;
+    if (wave) { qo = (float4*)take(N * 16); qd = (float4*)take(N * 16); qi = (int2*)take(N * 8); qh = (int4*)take(N * 32); qw = (unsigned*)take(8); }
+#define TR_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaStreamSynchronize(d.stream); return fail(c, XNART_ERR_CUDA, std::string(#expr " failed: ") + cudaGetErrorString(_e)); } } while (0)
+    if (ignore2) TR_TRY(cudaMemcpyAsync(di, ignore2, N * 8, cudaMemcpyHostToDevice, d.stream));
     TR_TRY(cudaMemcpyAsync(dr, rays6, N * 24, cudaMemcpyHostToDevice, d.stream));
     TR_TRY(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, d.stream));
-    if (useWave(c, d)) {
+    if (wave) {
         // same persistent kernel as the frame path: pack -> trace -> unpack
-        TR_TRY(cudaMalloc(&qo, N * 16)); TR_TRY(cudaMalloc(&qd, N * 16)); TR_TRY(cudaMalloc(&qi, N * 8)); TR_TRY(cudaMalloc(&qh, N * 32));
-        TR_TRY(cudaMalloc(&qw, 8));
         const unsigned words[2] = {(unsigned)N, 0u};
         TR_TRY(cudaMemcpyAsync(qw, words, 8, cudaMemcpyHostToDevice, d.stream));
         TR_TRY(launchPackRays(dr, di, n, qo, qd, qi, d.smCount * 8, d.stream));
@@ -1236,7 +1351,6 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
     TR_TRY(cudaMemcpyAsync(h, d.counters, sizeof h, cudaMemcpyDeviceToHost, d.stream));
     TR_TRY(cudaStreamSynchronize(d.stream));
 #undef TR_TRY
-    cleanup();
     XnartCounters t{};
     t.raysPrimary = (uint64_t)n; t.hits = h[CTR_HITS];
     t.nBox = h[CTR_NBOX]; t.nTriRef = h[CTR_NTRIREF]; t.nTriCulled = h[CTR_NTRICULLED]; t.nTriFull = h[CTR_NTRIFULL];
@@ -1252,7 +1366,20 @@ int32_t xnart_get_counters(XnartCtx* c, XnartCounters* out) {
     return rc;
 }
 
-float xnart_progress(XnartCtx* c) { return c ? c->progress.load() : 0.0f; }
+// RayTracer.Progress (RayTracer.cs:43-46: scanline / Height, polled from the game thread every 3 s, Game1.cs:331-341).
+// While a blocking render call is in flight the kernels report the pixels they have finished into one page-locked word
+// per in-flight state; may be called from any thread.
+float xnart_progress(XnartCtx* c) {
+    if (!c) return 0.0f;
+    if (!c->rendering.load()) return c->progress.load();
+    const unsigned long long total = c->progressTotal.load();
+    if (total == 0) return 0.0f;
+    unsigned long long done = 0;
+    for (const DeviceState& d : c->devs)
+        if (d.progressHost) done += *reinterpret_cast<volatile unsigned long long*>(d.progressHost);
+    const double f = (double)done / (double)total;
+    return (float)(f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f));
+}
 
 int64_t xnart_kernel_launches(XnartCtx* c) { return c ? c->launches.load() : 0; }
 

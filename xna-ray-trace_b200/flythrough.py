@@ -95,7 +95,7 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
         free_q, work_q = queue.Queue(), queue.Queue()
         for _ in range(3):
             free_q.put(torch.empty((world,) + unit_shape, dtype=unit_dtype, pin_memory=True))
-        failure = []
+        failure, busy = [], [0.0]
 
         def write_loop():
             while True:
@@ -105,6 +105,7 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
                 buf, ev, r0, cnt = item
                 try:
                     ev.synchronize()
+                    tw = time.perf_counter()
                     host = buf.numpy()
                     for k in range(cnt):
                         for q in range(world):
@@ -113,6 +114,7 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
                                     sink.AddFrameBits(host[q, k])
                                 else:
                                     sink.AddFrame(host[q, k].view(np.uint32))
+                    busy[0] += time.perf_counter() - tw
                 except Exception as e:   # e.g. disk full: keep draining so the render loop never blocks
                     failure.append(e)
                 free_q.put(buf)
@@ -165,6 +167,7 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
             x.set_option(records.OPT_KEEP_COUNTERS, 0)
             raise failure[0]
     secs = time.perf_counter() - t0
+    render_flythrough.last_sink_busy_s = busy[0] if writer is not None else None   # seconds the sink spent in AddFrame*
     rays = x.counters().rays
     x.set_option(records.OPT_KEEP_COUNTERS, 0)
     return len(mine), rays, secs

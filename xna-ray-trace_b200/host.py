@@ -141,15 +141,34 @@ class OctreeSpatialManager:
         self.built = False
 
     def Build(self):  # OctreeSpatialManager.cs:64-99
+        """Rebuilds from `Bodies`, as the reference does on every call: the backend's object list is cleared first, so a
+        second Build() (after appending a body, say) does not duplicate the scene."""
+        self.backend.clear_objects()
+        self._poses = []
         for obj in self.Bodies:
             for m in obj.Meshes:
                 m.Init(self.backend)
             self.backend.add_object([m._ids[self.backend] for m in obj.Meshes], obj.World, obj.InverseWorld, obj.BoundingBox)
+            self._poses.append((tuple(obj.Position), tuple(obj.Rotation), tuple(obj.Scale)))
+        self._built_bodies = list(self.Bodies)
         self.backend.build_scene(self.itemTreshold)
         self.built = True
 
+    def _sync_transforms(self):
+        """The reference reads SceneObject.World / InverseWorld per ray (OctreeSpatialManager.cs:358-364): a body moved
+        after Build() renders at its new pose, with the octree it was built with.  Poses that changed since the last
+        upload are sent to the backend (xnart_set_object_transform); bodies added or removed need a new Build()."""
+        if not self.built:
+            return
+        for i, obj in enumerate(self._built_bodies):
+            pose = (tuple(obj.Position), tuple(obj.Rotation), tuple(obj.Scale))
+            if pose != self._poses[i]:
+                self.backend.set_object_transform(i, obj.World, obj.InverseWorld)
+                self._poses[i] = pose
+
     def GetRayIntersection(self, ray_position, ray_direction, ignoreTriangle=None):
         """ISpatialManager.GetRayIntersection for one ray; ignoreTriangle = (Mesh, triangle index) or None."""
+        self._sync_transforms()
         ign = None
         if ignoreTriangle is not None:
             ign = [[ignoreTriangle[0]._ids[self.backend], ignoreTriangle[1]]]
@@ -290,6 +309,7 @@ class RayTracer:
         err = None
         try:
             be = self.CurrentScene.backend
+            self.CurrentScene._sync_transforms()
             w, h = self.Viewport
             be.set_lights([L._record() for L in self.Lights])
             frame = make_frame(self.CurrentCamera.View, self.CurrentCamera.Projection, w, h,

@@ -1,5 +1,5 @@
-"""Mesh ingest: ASCII FBX 6.1 -> Triangle records, following the conventions of the
-reference's build-time content processor.
+"""Mesh ingest: FBX 6.x (ASCII 6.1 and binary 6100) -> Triangle records, following the
+conventions of the reference's build-time content processor.
 
 The reference bakes its models at BUILD time: XNA's closed-source `FbxImporter` turns an .fbx into a
 `NodeContent` tree and `TracerModelProcessor` (RayTracePipeline/TracerModelProcessor.cs) walks it:
@@ -14,8 +14,9 @@ The reference bakes its models at BUILD time: XNA's closed-source `FbxImporter` 
     always contains the origin.
 
 This module restates the second and third bullet exactly (binary32, XNA operator order via xna.py) and
-replaces the closed importer by a small reader for the ASCII FBX 6.1 files the reference ships
-(`RayTraceProjectContent/*.fbx`: Blender exports).  What the closed importer does to axes, winding and
+replaces the closed importer by a small reader for the FBX files the reference ships: ASCII FBX 6.1
+(`RayTraceProjectContent/*.fbx`: Blender exports) and binary FBX 6100 (`Crate_Fragile.FBX`, the Free_crate asset of
+BASELINE.json configs[0..1], and the other 3ds Max exports); both parse into the same node tree.  What the closed importer does to axes, winding and
 texture coordinates cannot be checked here — PARITY UNPINNED for those three choices, which are made as
 SURVEY.md Appendix A.3/A.4 recommends and kept in one place (`IMPORTER`):
 
@@ -25,11 +26,16 @@ SURVEY.md Appendix A.3/A.4 recommends and kept in one place (`IMPORTER`):
     seen from outside (XNA's front faces are clockwise);
   * v -> 1 - v for texture coordinates (FBX has v up, XNA v down).
 
-The binary FBX files of the reference (`Crate_Fragile.FBX` etc.) are not read; the crate's geometry is
-restated in scenes.py from SURVEY.md A.4.
+Scene graph: a mesh node's transform is composed with its parents' (`Connections`: local * parent * ... in row-vector
+order).  What this reader does not model — PreRotation / PostRotation with RotationActive, a RotationOrder other than
+XYZ, non-zero Geometric* offsets, pivots — raises NotImplementedError instead of silently placing the mesh wrongly.
+
+`scenes.crate_scene` restates the crate's geometry from SURVEY.md A.4 (the asset does not travel to the GPU box);
+tests/test_ingest.py checks that restatement against the geometry read from `Crate_Fragile.FBX` itself.
 """
 import math
 import re
+import struct
 
 import numpy as np
 
@@ -113,6 +119,90 @@ def parse_fbx_ascii(text):
     return root
 
 
+# ---------------------------------------------------------------------------------------------
+# binary FBX 6100 reader (same FbxNode tree as the ASCII reader)
+# ---------------------------------------------------------------------------------------------
+_BIN_MAGIC = b"Kaydara FBX Binary  \x00\x1a\x00"
+
+
+def _bin_name(v):
+    """Binary files store object names as `Name\0\1Class`; the ASCII form is `Class::Name`."""
+    if isinstance(v, str) and "\x00\x01" in v:
+        name, cls = v.split("\x00\x01", 1)
+        return cls + "::" + name
+    return v
+
+
+def parse_fbx_binary(data):
+    """Node record: u32 endOffset, u32 numProperties, u32 propertyListLen, u8 nameLen, name, properties, nested
+    records up to endOffset, the list closed by a 13-byte null record.  Property = type byte + payload:
+    Y i16, C u8, I i32, F f32, D f64, L i64, S / R u32 length + bytes, and (7000+) f d l i b arrays."""
+    import zlib
+
+    if data[:len(_BIN_MAGIC)] != _BIN_MAGIC:
+        raise ValueError("not a binary FBX file")
+    version = struct.unpack_from("<I", data, 23)[0]
+    if version >= 7500:
+        raise NotImplementedError("binary FBX %d uses 64-bit node records" % version)
+    scalar = {"Y": "<h", "C": "<B", "I": "<i", "F": "<f", "D": "<d", "L": "<q"}
+    array = {"f": "<f4", "d": "<f8", "l": "<i8", "i": "<i4", "b": "u1"}
+
+    def node_at(pos):
+        end, nprop, plen, nlen = struct.unpack_from("<IIIB", data, pos)
+        if end == 0:
+            return None, pos + 13
+        name = data[pos + 13:pos + 13 + nlen].decode("ascii", "replace")
+        q = pos + 13 + nlen
+        vals = []
+        for _ in range(nprop):
+            t = chr(data[q])
+            q += 1
+            if t in scalar:
+                v = struct.unpack_from(scalar[t], data, q)[0]
+                q += struct.calcsize(scalar[t])
+                vals.append(float(v) if t in "FD" else int(v))
+            elif t in "SR":
+                n = struct.unpack_from("<I", data, q)[0]
+                raw = data[q + 4:q + 4 + n]
+                q += 4 + n
+                vals.append(_bin_name(raw.decode("latin-1")) if t == "S" else raw)
+            elif t in array:
+                cnt, enc, clen = struct.unpack_from("<III", data, q)
+                raw = data[q + 12:q + 12 + clen]
+                q += 12 + clen
+                if enc == 1:
+                    raw = zlib.decompress(raw)
+                a = np.frombuffer(raw, dtype=array[t], count=cnt)
+                vals.extend(float(x) for x in a) if t in "fd" else vals.extend(int(x) for x in a)
+            else:
+                raise ValueError("unknown FBX property type %r at offset %d" % (t, q - 1))
+        node = FbxNode(name, vals)
+        while q < end:
+            child, q = node_at(q)
+            if child is None:
+                break
+            node.children.append(child)
+        return node, end
+
+    root = FbxNode("", [version])
+    pos = 27
+    while pos + 13 <= len(data):
+        n, pos = node_at(pos)
+        if n is None:
+            break
+        root.children.append(n)
+    return root
+
+
+def parse_fbx_file(path):
+    """Node tree of an FBX 6.x file, ASCII or binary."""
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:len(_BIN_MAGIC)] == _BIN_MAGIC:
+        return parse_fbx_binary(data)
+    return parse_fbx_ascii(data.decode("utf-8", "replace"))
+
+
 def _lcl(props, key, default):
     for p in props.all("Property") if props is not None else []:
         if p.values and p.values[0] == key:
@@ -132,22 +222,83 @@ def _layer(model, elem, data, index):
     return mapping, ref, d, (np.asarray(idx.values, dtype=np.int64) if idx is not None and idx.values else None)
 
 
+def _prop3(props, key):
+    for p in props.all("Property") if props is not None else []:
+        if p.values and p.values[0] == key and len(p.values) >= 3:
+            try:
+                return tuple(float(v) for v in p.values[-3:])
+            except (TypeError, ValueError):
+                return None
+    return None
+
+
+def _prop1(props, key):
+    for p in props.all("Property") if props is not None else []:
+        if p.values and p.values[0] == key:
+            return p.values[-1]
+    return None
+
+
+def _check_supported(name, props):
+    """Transform features this reader does not model must not pass silently (a mesh would land in the wrong pose)."""
+    for key in ("GeometricTranslation", "GeometricRotation", "RotationOffset", "RotationPivot", "ScalingOffset", "ScalingPivot"):
+        v = _prop3(props, key)
+        if v is not None and any(abs(c) > 0.0 for c in v):
+            raise NotImplementedError("%s: non-zero %s is not supported" % (name, key))
+    g = _prop3(props, "GeometricScaling")
+    if g is not None and any(abs(c - 1.0) > 0.0 for c in g):
+        raise NotImplementedError("%s: GeometricScaling is not supported" % name)
+    if _prop1(props, "RotationActive") in (1, True):
+        for key in ("PreRotation", "PostRotation"):
+            v = _prop3(props, key)
+            if v is not None and any(abs(c) > 0.0 for c in v):
+                raise NotImplementedError("%s: %s with RotationActive is not supported" % (name, key))
+    ro = _prop1(props, "RotationOrder")
+    if ro not in (None, 0, "0"):
+        raise NotImplementedError("%s: RotationOrder %r is not supported (only XYZ)" % (name, ro))
+
+
 def read_fbx_meshes(path):
-    """Mesh models of an ASCII FBX 6.1 file: list of dicts with name, lcl (translation, rotation in degrees,
-    scaling), vertices (N, 3), polygons (lists of vertex indices), normals / uvs as (mapping, reference, data,
-    index)."""
-    with open(path, "r", errors="replace") as f:
-        head = f.read(64)
-        if "Kaydara FBX Binary" in head:
-            raise ValueError("%s is a binary FBX file; only ASCII FBX 6.1 is read" % path)
-        text = head + f.read()
-    root = parse_fbx_ascii(text)
+    """Mesh models of an FBX 6.x file (ASCII or binary): list of dicts with name, lcl (translation, rotation in degrees,
+    scaling), parents (the lcl triples of the chain of parent models, nearest first), vertices (N, 3), polygons
+    (lists of vertex indices), normals / uvs as (mapping, reference, data, index), axes (UpAxis, UpAxisSign,
+    FrontAxis, FrontAxisSign, CoordAxis, CoordAxisSign, UnitScaleFactor from GlobalSettings, when present)."""
+    root = parse_fbx_file(path)
     objects = root.child("Objects")
-    out = []
+    models = {}
     for m in (objects.all("Model") if objects is not None else []):
+        if m.values:
+            models[str(m.values[0])] = m
+    parent_of = {}
+    conns = root.child("Connections")
+    for c in (conns.all("Connect") if conns is not None else []):
+        if len(c.values) >= 3 and c.values[0] == "OO":
+            parent_of.setdefault(str(c.values[1]), str(c.values[2]))
+    axes = {}
+    gs = objects.child("GlobalSettings") if objects is not None else None
+    gp = gs.child("Properties60") if gs is not None else None
+    for key in ("UpAxis", "UpAxisSign", "FrontAxis", "FrontAxisSign", "CoordAxis", "CoordAxisSign", "UnitScaleFactor"):
+        v = _prop1(gp, key)
+        if v is not None:
+            axes[key] = v
+
+    def lcl_of(model):
+        props = model.child("Properties60")
+        return (_lcl(props, "Lcl Translation", (0.0, 0.0, 0.0)), _lcl(props, "Lcl Rotation", (0.0, 0.0, 0.0)),
+                _lcl(props, "Lcl Scaling", (1.0, 1.0, 1.0)))
+
+    out = []
+    for key, m in models.items():
         if len(m.values) < 2 or m.values[1] != "Mesh" or m.child("Vertices") is None:
             continue
         props = m.child("Properties60")
+        _check_supported(key, props)
+        parents, p, seen = [], parent_of.get(key), set()
+        while p is not None and p in models and p not in seen:      # "Model::Scene" (the root) is not in Objects
+            seen.add(p)
+            _check_supported(p, models[p].child("Properties60"))
+            parents.append(lcl_of(models[p]))
+            p = parent_of.get(p)
         verts = np.asarray(m.child("Vertices").values, dtype=np.float64).reshape(-1, 3)
         polys, cur = [], []
         for i in m.child("PolygonVertexIndex").values:
@@ -163,10 +314,14 @@ def read_fbx_meshes(path):
             normals = (normals[0], normals[1], normals[2].reshape(-1, 3), normals[3])
         if uvs is not None:
             uvs = (uvs[0], uvs[1], uvs[2].reshape(-1, 2), uvs[3])
-        out.append({"name": str(m.values[0]).replace("Model::", ""),
-                    "lcl": (_lcl(props, "Lcl Translation", (0.0, 0.0, 0.0)), _lcl(props, "Lcl Rotation", (0.0, 0.0, 0.0)),
-                            _lcl(props, "Lcl Scaling", (1.0, 1.0, 1.0))),
-                    "vertices": verts, "polygons": polys, "normals": normals, "uvs": uvs})
+        tex = None
+        for t in (objects.all("Texture") if objects is not None else []):
+            fn = t.child("RelativeFilename") or t.child("FileName")
+            if fn is not None and fn.values:
+                tex = str(fn.values[0])
+                break
+        out.append({"name": key.replace("Model::", ""), "lcl": lcl_of(m), "parents": parents,
+                    "vertices": verts, "polygons": polys, "normals": normals, "uvs": uvs, "axes": axes, "texture": tex})
     return out
 
 
@@ -210,7 +365,10 @@ def process_model(meshes, scale=1.0, rotation_deg=(0.0, 0.0, 0.0), diffuse_color
     color = np.asarray(diffuse_color, dtype=F) / F(255.0)          # Color.ToVector4()
     out = []
     for m in meshes:
-        absolute = xna.multiply(_node_transform(m["lcl"]), scene)  # MeshContent.AbsoluteTransform
+        local = _node_transform(m["lcl"])
+        for parent in m.get("parents", ()):                        # row vectors: local * parent * grandparent * ...
+            local = xna.multiply(local, _node_transform(parent))
+        absolute = xna.multiply(local, scene)                      # MeshContent.AbsoluteTransform
         inv_t = xna.invert(absolute).T.copy()                      # Transpose(Invert(absoluteTransform)) (:141)
         corners = []
         pv = 0
@@ -263,5 +421,5 @@ def create_bounding_box(tris):
 
 
 def load_model(path, **processor_parameters):
-    """Content.Load<Model>(name).Tag["Meshes"] for an ASCII FBX file: [(triangles, meshBoundingBox), ...]."""
+    """Content.Load<Model>(name).Tag["Meshes"] for an FBX 6.x file (ASCII or binary): [(triangles, meshBoundingBox), ...]."""
     return process_model(read_fbx_meshes(path), **processor_parameters)

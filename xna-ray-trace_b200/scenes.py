@@ -202,26 +202,50 @@ def _orient_outward(v1, v2, v3, center):
     return v1, v2n.astype(np.float32), v3n.astype(np.float32), flip
 
 
-def crate_triangles():
-    """Crate_Fragile.FBX geometry: 8 vertices, 6 quads, scale 0.6, Z-up -> Y-up."""
-    h, H = 19.685039520263672, 39.370079040527344
-    verts = np.array([(-h, -h, 0), (-h, -h, H), (h, -h, H), (h, -h, 0), (h, h, 0), (h, h, H), (-h, h, H), (-h, h, 0)],
-                     dtype=np.float64) * 0.6
+def _crate_from(verts64, quads, quv):
+    """The crate mesh from FBX control points (Z up), quads and per-corner UVs: content scale 0.6
+    (RayTraceProjectContent.contentproj:69), Z-up -> Y-up, fan triangulation with the winding reversed."""
+    verts = np.asarray(verts64, dtype=np.float64) * 0.6
     verts = np.stack([verts[:, 0], verts[:, 2], -verts[:, 1]], axis=1).astype(np.float32)  # (x, z, -y)
-    quads = [(3, 2, 1, 0), (7, 6, 5, 4), (0, 1, 6, 7), (4, 5, 2, 3), (2, 5, 6, 1), (4, 3, 0, 7)]
-    quv = np.array([(1, 0), (1, 1), (0, 1), (0, 0)], dtype=np.float32)
     v1, v2, v3, u1, u2, u3 = [], [], [], [], [], []
-    for q in quads:
+    for qi, q in enumerate(quads):
+        uvq = quv[qi] if np.ndim(quv) == 3 else quv
         for a, b, c in ((0, 1, 2), (0, 2, 3)):
             # reversed winding so that Cross(e2, e1) is the outward normal
             v1.append(verts[q[a]]); v2.append(verts[q[c]]); v3.append(verts[q[b]])
-            u1.append(quv[a]); u2.append(quv[c]); u3.append(quv[b])
+            u1.append(uvq[a]); u2.append(uvq[c]); u3.append(uvq[b])
     v1, v2, v3 = (np.array(a, dtype=np.float32) for a in (v1, v2, v3))
     center = verts.mean(axis=0)
     sn = _normalize(_cross((v3 - v1).astype(np.float32), (v2 - v1).astype(np.float32)))
     cen = ((v1 + v2 + v3) / F(3.0)) - center
     assert ((sn * cen).sum(axis=1) > 0).all(), "crate winding must face outward"
-    return make_triangles(v1, v2, v3, uv1=np.array(u1), uv2=np.array(u2), uv3=np.array(u3), color=(1, 1, 1, 1))
+    return make_triangles(v1, v2, v3, uv1=np.array(u1, dtype=np.float32), uv2=np.array(u2, dtype=np.float32),
+                          uv3=np.array(u3, dtype=np.float32), color=(1, 1, 1, 1))
+
+
+def crate_triangles():
+    """Crate_Fragile.FBX geometry: 8 vertices, 6 quads, scale 0.6, Z-up -> Y-up.  The asset does not
+    travel to the GPU box, so its numbers are restated here; tests/test_ingest.py checks them against the file."""
+    h, H = 19.685039520263672, 39.370079040527344
+    verts = [(-h, -h, 0), (-h, -h, H), (h, -h, H), (h, -h, 0), (h, h, 0), (h, h, H), (-h, h, H), (-h, h, 0)]
+    quads = [(3, 2, 1, 0), (7, 6, 5, 4), (0, 1, 6, 7), (4, 5, 2, 3), (2, 5, 6, 1), (4, 3, 0, 7)]
+    quv = np.array([(1, 0), (1, 1), (0, 1), (0, 0)], dtype=np.float32)
+    return _crate_from(verts, quads, quv)
+
+
+def crate_triangles_from_fbx(path):
+    """The same mesh with control points, polygons and UVs read from the shipped binary asset
+    (RayTraceProjectContent/Crate_Fragile.FBX, ingest.read_fbx_meshes)."""
+    from . import ingest
+
+    (m,) = ingest.read_fbx_meshes(path)
+    mapping, ref, data, index = m["uvs"]
+    assert mapping == "ByPolygonVertex" and all(len(q) == 4 for q in m["polygons"])
+    pv, quv = 0, []
+    for q in m["polygons"]:
+        quv.append([data[int(index[pv + k])] if index is not None else data[pv + k] for k in range(4)])
+        pv += 4
+    return _crate_from(m["vertices"], m["polygons"], np.asarray(quv, dtype=np.float32))
 
 
 def ground_triangles(half=60.0, y=0.0, color=(1, 1, 1, 1)):
