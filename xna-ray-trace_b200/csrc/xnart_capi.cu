@@ -289,7 +289,8 @@ int32_t xnart_add_mesh(XnartCtx* c, const XnartTriangle* tris, int64_t nTri, con
                 if (tris[i].v1[k] != tris[i].v1[k] || tris[i].v2[k] != tris[i].v2[k] || tris[i].v3[k] != tris[i].v3[k]) nan = true;
         if (nan) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_mesh: NaN vertex coordinate");
     }
-    std::lock_guard<std::mutex> lk(c->renderMutex);
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");   // RayTracer.cs:62-63
     HostMesh m;
     m.nTri = nTri;
     std::memcpy(m.box.mn, box, 12);
@@ -318,7 +319,8 @@ int32_t xnart_add_object(XnartCtx* c, const int32_t* meshIds, int32_t nMesh, con
     for (int a = 0; a < 16; a++)
         if (world[a] != world[a] || inverseWorld[a] != inverseWorld[a]) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: NaN in a matrix");
     for (int a = 0; a < 6; a++) if (localBox[a] != localBox[a]) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: NaN in localBoxMinMax");
-    std::lock_guard<std::mutex> lk(c->renderMutex);
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");   // RayTracer.cs:62-63
     HostObj o;
     for (int i = 0; i < nMesh; i++) {
         if (meshIds[i] < 0 || meshIds[i] >= (int)c->meshes.size()) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_add_object: bad mesh id");
@@ -388,7 +390,8 @@ int32_t xnart_set_object_transform(XnartCtx* c, int32_t objId, const float world
 
 int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
     if (!c || itemThreshold < 0) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_build_scene: bad arguments");
-    std::lock_guard<std::mutex> lk(c->renderMutex);
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");   // RayTracer.cs:62-63
     c->built = false;   // stays false if anything below fails: a half-uploaded scene must never be rendered
     int rc = buildSceneOctree(c->objs, itemThreshold, c->sceneTree, c->err);
     if (rc != XNART_OK) return rc;
@@ -606,7 +609,8 @@ int32_t xnart_set_lights(XnartCtx* c, const XnartLight* lights, int32_t n) {
     for (int i = 0; i < n; i++)
         if (lights[i].kind != XNART_LIGHT_SPOT && lights[i].kind != XNART_LIGHT_DIRECTIONAL)
             return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_set_lights: unknown light kind");
-    std::lock_guard<std::mutex> lk(c->renderMutex);
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");   // RayTracer.cs:62-63
     c->lights.assign(lights, lights + n);
     c->lightsDirty = true;
     return XNART_OK;
