@@ -149,28 +149,21 @@ def alg_flops(c):
 
 def bind_to_gpu_numa_node(local_rank):
     """Page-locked frame buffers should live on the NUMA node the GPU hangs off (8 ranks each writing tens of
-    GB/s into host memory otherwise all land on one node): restrict this process to that node's CPUs before any
-    pinned allocation is made.  Best effort; returns the node or None."""
+    GB/s into host memory otherwise all land wherever the ranks happened to start): restrict this process to the
+    CPUs NVML names as the GPU's ideal affinity before any pinned allocation is made.  Best effort; returns the
+    number of CPUs bound to, or None."""
     try:
         import pynvml
 
         pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
-        bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:
-            bus = bus[4:]
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
         allowed = cpus & os.sched_getaffinity(0)
-        if allowed:
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
             os.sched_setaffinity(0, allowed)
-            return node
+            return len(allowed)
     except Exception:
         pass
     return None
@@ -594,7 +587,7 @@ def main():
                                        if gather_mode == "p2p" else "async NCCL gather")) if world > 1 else "single GPU",
                     "l2": "each step writes %d MB of frames (ring of 2 steps) — larger than the 126 MB L2 — from %d different cameras; the "
                           "scene itself is 1.5 KB in the constant bank and cannot be made larger than a cache" % (half_bytes >> 20, ORBIT),
-                    "numa_node": numa, "cpu_cores": os.cpu_count()},
+                    "cpus_bound_near_gpu": numa, "cpu_cores": os.cpu_count()},
             "frames_per_s": world * FPS * args.steps / (ms * 1e-3),
             "rays_per_frame": total_rays / (world * FPS * max(1, args.steps)),
             "checksum": checksum,
