@@ -667,3 +667,37 @@ def test_multi_device_context_splits_one_frame(X):
     assert np.array_equal(y1.render_frame(fg), y2.render_frame(fg))
     for c in (x1, x2, y1, y2):
         c.close()
+
+
+def test_sub_shards_over_in_flight_states(X, oracle_mod):
+    """Deep scenes: a context with k in-flight states on one GPU renders ONE frame (or one rank's shard of it) as k
+    sub-shards of scanline bands side by side (xnart_render_frame_device).  Pixels and ray counts are those of a
+    single-state context."""
+    import torch
+
+    s = make_scene("grid")
+    x1 = X.Xnart(devices=(0,))
+    x1.set_option(records.OPT_TRAVERSAL, 2)
+    scenes.upload(x1, s)
+    x3 = X.Xnart(devices=(0,), frames_in_flight=3)
+    x3.set_option(records.OPT_TRAVERSAL, 2)
+    scenes.upload(x3, s)
+    for wh, kw in (((320, 200), {}), ((320, 200), dict(shard_index=1, shard_count=2, shard_band_rows=8)), ((203, 77), {}), ((64, 16), {})):
+        f = s.frame(*wh, **kw)
+        a = torch.zeros((wh[1], wh[0]), dtype=torch.int32, device="cuda:0")
+        b = torch.zeros_like(a)
+        x1.render_frame_device(f, a.data_ptr())
+        c1 = x1.counters()
+        x3.render_frame_device(f, b.data_ptr())
+        c3 = x3.counters()
+        assert torch.equal(a, b), (wh, kw)
+        for k in ("raysPrimary", "raysShadow", "raysReflection", "hits", "pixels"):
+            assert getattr(c1, k) == getattr(c3, k), (k, wh, kw)
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    f = s.frame(320, 200)
+    b = torch.zeros((200, 320), dtype=torch.int32, device="cuda:0")
+    x3.render_frame_device(f, b.data_ptr())
+    assert np.array_equal(o.render_frame(f, n_threads=8), b.cpu().numpy().view(np.uint32))
+    x1.close()
+    x3.close()

@@ -971,15 +971,43 @@ int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* de
     DeviceState& d = c->devs[0];
     CU_TRY(c, cudaSetDevice(d.dev));
     cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : d.stream;
+    // Deep scenes (wavefront path): a frame is ~30 launches, each ending in the serial tail of its longest rays.  With k
+    // in-flight states on this GPU the shard is rendered as k sub-shards of scanline bands side by side — sub-shard j of
+    // shard (i of n) is shard (i + j*n of k*n), a subset of the same bands — so the tails of one overlap the bulk of the
+    // others.  What a rank of a tile split gains with k = 2 is in DESIGN.md section 7.
+    std::vector<int> states;
+    for (int i = 0; i < (int)c->devs.size(); i++)
+        if (c->devs[i].dev == d.dev) states.push_back(i);
+    const int sc = frame->shardCount > 1 ? frame->shardCount : 1;
+    const int si = sc > 1 ? frame->shardIndex : 0, br = sc > 1 ? frame->shardBandRows : 8;
+    const int k = (int)states.size();
+    const bool sub = k > 1 && useWave(c, d) && (long long)br * sc * k <= (long long)frame->vpH;
+    auto enqueueAll = [&]() -> int {
+        if (!sub) return enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
+        CU_TRY(c, cudaEventRecord(d.evRendered[0], st));
+        for (int j = 0; j < k; j++) {
+            DeviceState& dj = c->devs[states[(size_t)j]];
+            cudaStream_t sj = (j == 0) ? st : dj.stream;
+            if (sj != st) CU_TRY(c, cudaStreamWaitEvent(sj, d.evRendered[0], 0));
+            XnartFrame f = *frame;
+            f.shardCount = sc * k; f.shardIndex = si + j * sc; f.shardBandRows = br;
+            int r = enqueueFrame(c, dj, f, (uint32_t*)devOut, sj);
+            if (r != XNART_OK) return r;
+            if (sj != st) {
+                CU_TRY(c, cudaEventRecord(dj.evRendered[1], sj));
+                CU_TRY(c, cudaStreamWaitEvent(st, dj.evRendered[1], 0));
+            }
+        }
+        return XNART_OK;
+    };
     if (cudaStream) {   // asynchronous: the caller owns completion, nothing to poll
         c->progress = 0.0f;
-        rc = enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
+        rc = enqueueAll();
         if (rc == XNART_OK) c->progress = 1.0f;
         return rc;
     }
-    const int sc = frame->shardCount > 1 ? frame->shardCount : 1;
-    ProgressScope ps(c, (unsigned long long)localRowsOf(frame->vpH, sc > 1 ? frame->shardIndex : 0, sc, sc > 1 ? frame->shardBandRows : 1) * (unsigned long long)frame->vpW);
-    rc = enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
+    ProgressScope ps(c, (unsigned long long)localRowsOf(frame->vpH, si, sc, br) * (unsigned long long)frame->vpW);
+    rc = enqueueAll();
     if (rc != XNART_OK) return rc;
     CU_TRY(c, cudaStreamSynchronize(st));
     c->last.msCopy = 0; c->last.msTotal = 0;
