@@ -123,6 +123,8 @@ enum {
                                     ray, which shortens the serial tail of deep levels (default 131072, 0 = never) */
     XNART_OPT_KEEP_COUNTERS = 10, /* 0/1 (default 0): 1 = render calls stop resetting the statistics, xnart_get_counters
                                     returns totals since the option was set (setting it, to 0 or 1, resets them) */
+    XNART_OPT_SPLIT_HIT_PCT = 12, /* wavefront path: a batch is split only if the closest-hit batch it descends from hit at most this
+                                    percentage of its rays (default 50): segments behind an early hit are wasted work in dense scenes */
     XNART_OPT_PATH_KERNEL = 9    /* 0/1 (default 1): small opaque scenes (single-leaf octrees that fit a kernel parameter,
                                     e.g. Free_crate) render a frame with ONE persistent launch: a thread follows a pixel's
                                     whole reflection chain, the scene is read from the constant bank (csrc/path.cu) */

@@ -124,6 +124,13 @@ struct TraceJob {
     // k_trace<.., false>.  Both kernels are launched, the one that does not apply exits at once.
     int4* outSplit;
     unsigned int splitMax;   // 0: never split
+    // Splitting pays when rays run their whole path without an accepted triangle (grazing a surface, leaving for the sky):
+    // the segments are then work the whole-ray walk would have done anyway.  Where most rays hit early (a dense soup) the
+    // segments behind the hit are wasted.  Hint: hits / rays of the closest-hit batch this one descends from (NULL: none);
+    // the batch is split only if hits * 100 <= rays * splitHitPct.
+    const unsigned int* hintHits;
+    const unsigned int* hintRays;
+    unsigned int splitHitPct;
 };
 constexpr int kSplit = 8;
 
@@ -175,6 +182,7 @@ struct DevArena {
     int4* hitSplit[2];   // split batches: kSplit records per ray of the level (<= splitMax rays)
     int4* shSplit[2];    // ... per shadow ray
     unsigned int splitMax;
+    unsigned int splitHitPct;   // see TraceJob
     unsigned int* shadowHits;   // [maxLevels+2] hits per level (= rays per shadow segment)
     unsigned int* fetch;        // [2*(maxLevels+2)] work counters of the trace launches
 };

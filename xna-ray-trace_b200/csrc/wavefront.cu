@@ -68,13 +68,25 @@ __global__ void __launch_bounds__(256) k_gen_primary(DevFrame F, DevArena A) {
 // list, profiles/r01h: 42 M warp instructions in 0.68 ms).  Cutting the ray into segments by entry
 // distance divides that serial walk by up to kSplit and gives the same answer (the first non-empty
 // segment's).  The instrumented build never splits: its counters are those of the canonical walk.
+// Is this batch traced as split queries?  Decided on the device (the batch size is only known there); the shade kernels
+// that read the results evaluate the same rule (isSplitBatch below).
+__device__ __forceinline__ bool splitRule(int nPairs, unsigned splitMax, unsigned nRays, const unsigned* hintHits, const unsigned* hintRays,
+                                          unsigned pct) {
+    if (splitMax == 0u || nRays > splitMax || nPairs != 1) return false;
+    if (hintHits == nullptr || hintRays == nullptr) return true;
+    return (unsigned long long)(*hintHits) * 100ull <= (unsigned long long)(*hintRays) * (unsigned long long)pct;
+}
+__device__ __forceinline__ bool isSplitJob(const DevScene& S, const TraceJob& J, unsigned nRays) {
+    return splitRule(S.nPairs, J.splitMax, nRays, J.hintHits, J.hintRays, J.splitHitPct);
+}
+
 template <bool COUNT, bool SPLIT>
 __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, TraceJob J, unsigned long long* __restrict__ counters) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned segCount = *J.segCount;
     const unsigned nRays = segCount * J.nSeg;
-    const bool splitBatch = !COUNT && J.splitMax != 0u && nRays <= J.splitMax && S.nPairs == 1;
+    const bool splitBatch = !COUNT && isSplitJob(S, J, nRays);
     if (splitBatch != SPLIT) return;
     const unsigned total = SPLIT ? nRays * (unsigned)kSplit : nRays;
     Seg seg;
@@ -271,8 +283,12 @@ __device__ __forceinline__ void fetchHit(const int4* __restrict__ plain, const i
         if (x.x >= 0) { a = x; b = p[2 * sgm + 1]; return; }
     }
 }
-__device__ __forceinline__ bool isSplitBatch(const DevScene& S, const DevArena& A, unsigned nRays) {
-    return A.splitMax != 0u && nRays <= A.splitMax && S.nPairs == 1;
+// level >= 0: the closest-hit batch of that level (hint = hits / rays of level - 1, none at level 0);
+// shadowOf >= 0: the shadow batch of that level (hint = hits / rays of the level's own closest-hit batch).
+__device__ __forceinline__ bool isSplitBatch(const DevScene& S, const DevArena& A, unsigned nRays, int level, int shadowOf) {
+    const int h = shadowOf >= 0 ? shadowOf : level - 1;
+    if (h < 0) return splitRule(S.nPairs, A.splitMax, nRays, nullptr, nullptr, A.splitHitPct);
+    return splitRule(S.nPairs, A.splitMax, nRays, &A.shadowHits[h], &A.levelCount[h], A.splitHitPct);
 }
 
 __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
@@ -282,7 +298,7 @@ __global__ void __launch_bounds__(256) k_shade_a(DevScene S, DevFrame F, DevAren
     if (blockIdx.x == 0 && threadIdx.x == 0) { A.levelBase[level + 1] = nextBase; reportProgress(F, level); }
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
     const int par = level & 1;
-    const bool splitL = isSplitBatch(S, A, count);
+    const bool splitL = isSplitBatch(S, A, count, level, -1);
     unsigned nHits = 0, nRefl = 0, nRefr = 0;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
@@ -344,9 +360,9 @@ __global__ void __launch_bounds__(256) k_shade_b(DevScene S, DevFrame F, DevAren
     const unsigned base = A.levelBase[level];
     const bool last = !(level < F.maxReflections);  // RayTracer.cs:545
     const int par = level & 1;
-    const bool splitL = isSplitBatch(S, A, count);
+    const bool splitL = isSplitBatch(S, A, count, level, -1);
     const unsigned nShadowHits = A.shadowHits[level];
-    const bool splitS = isSplitBatch(S, A, nShadowHits * (unsigned)F.nLights);
+    const bool splitS = isSplitBatch(S, A, nShadowHits * (unsigned)F.nLights, -1, level);
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         const unsigned node = base + idx;
         int4 ha, hb;

@@ -100,6 +100,7 @@ struct XnartCtx {
     int64_t arenaLimit = (int64_t)8 << 30;
     int traceSemantics = XNART_SEMANTICS_XNA40;
     bool chainResolve = true;   // XNART_OPT_CHAIN_RESOLVE: opaque scenes resolve a pixel's chain in one launch
+    int64_t splitHitPct = 50;   // XNART_OPT_SPLIT_HIT_PCT: split only batches whose parent batch hit at most this share of its rays
     int64_t splitRays = 131072;  // XNART_OPT_SPLIT_RAYS: batches up to this many rays are traced as segment queries (0 = never)
     bool overlapLevels = true;  // XNART_OPT_OVERLAP_LEVELS: side stream for the shadow batches of the wavefront path
     // XNART_OPT_FUSE_FRAME: one cooperative launch per frame on shallow scenes.  Off by default: measured
@@ -264,6 +265,9 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
             c->last = XnartCounters{};
             return XNART_OK;
         }
+        case XNART_OPT_SPLIT_HIT_PCT:
+            if (value < 0 || value > 100) return fail(c, XNART_ERR_INVALID_ARGUMENT, "percentage out of range");
+            c->splitHitPct = value; return XNART_OK;
         case XNART_OPT_TRAVERSAL:
             if (value < 0 || value > 2) return fail(c, XNART_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
             c->traversalMode = (int)value; return XNART_OK;
@@ -690,6 +694,7 @@ static int ensureArena(XnartCtx* c, DeviceState& d, unsigned nodes, unsigned ray
         A.shSplit[q] = (wave && splitMax) ? (int4*)take((size_t)splitMax * kSplit * 32) : nullptr;
     }
     A.splitMax = splitMax;
+    A.splitHitPct = (unsigned)c->splitHitPct;
     A.levelCount = d.levelWords;
     A.levelBase = d.levelWords + (kMaxLevels + 2);
     A.overflow = d.levelWords + 2 * (kMaxLevels + 2);
@@ -852,7 +857,8 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
             TraceJob J;
             J.rayO = A.rayO[in]; J.rayD = A.rayD[in]; J.rayIgn = A.rayIgn[in]; J.out = A.hit[in];
             J.segCount = &A.levelCount[L]; J.fetch = &A.fetch[2 * L]; J.nSeg = 1; J.segStride = 0;
-            J.outSplit = A.hitSplit[in]; J.splitMax = A.splitMax;
+            J.outSplit = A.hitSplit[in]; J.splitMax = A.splitMax; J.splitHitPct = A.splitHitPct;
+            J.hintHits = L > 0 ? &A.shadowHits[L - 1] : nullptr; J.hintRays = L > 0 ? &A.levelCount[L - 1] : nullptr;
             CU_TRY(c, launchTrace(d.scene, J, d.counters, tb, c->countKernels, st));
             CU_TRY(c, launchShadeA(d.scene, F, A, d.lights, L, (long long)ub, maxBlocks, st));
             c->launches += 2;
@@ -863,7 +869,8 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
                 TraceJob Sj;
                 Sj.rayO = A.shO[in]; Sj.rayD = A.shD[in]; Sj.rayIgn = A.shIgn[in]; Sj.out = A.shHit[in];
                 Sj.segCount = &A.shadowHits[L]; Sj.fetch = &A.fetch[2 * L + 1]; Sj.nSeg = (unsigned)F.nLights; Sj.segStride = A.rayCapacity;
-                Sj.outSplit = A.shSplit[in]; Sj.splitMax = A.splitMax;
+                Sj.outSplit = A.shSplit[in]; Sj.splitMax = A.splitMax; Sj.splitHitPct = A.splitHitPct;
+                Sj.hintHits = &A.shadowHits[L]; Sj.hintRays = &A.levelCount[L];
                 CU_TRY(c, launchTrace(d.scene, Sj, d.counters, tb, c->countKernels, ss));
                 c->launches++;
             }
@@ -1364,7 +1371,7 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
         TR_TRY(launchPackRays(dr, di, n, qo, qd, qi, d.smCount * 8, d.stream));
         TraceJob J;
         J.rayO = qo; J.rayD = qd; J.rayIgn = qi; J.out = qh; J.segCount = qw; J.fetch = qw + 1; J.nSeg = 1; J.segStride = 0;
-        J.outSplit = nullptr; J.splitMax = 0;
+        J.outSplit = nullptr; J.splitMax = 0; J.hintHits = J.hintRays = nullptr; J.splitHitPct = 100;
         TR_TRY(launchTrace(d.scene, J, d.counters, c->countKernels ? d.traceBlocksCount : d.traceBlocks, c->countKernels, d.stream));
         TR_TRY(launchUnpackHits(d.scene, qh, n, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, d.stream));
         c->launches += 3;

@@ -105,6 +105,7 @@ SEMANTICS_XNA40, SEMANTICS_MONOGAME = 0, 1
 OPT_COUNTERS, OPT_ARENA_BYTES, OPT_SEMANTICS, OPT_TRAVERSAL, OPT_FUSE_FRAME, OPT_OVERLAP_LEVELS, OPT_SPLIT_RAYS, OPT_CHAIN_RESOLVE = 1, 2, 3, 4, 5, 6, 7, 8
 OPT_PATH_KERNEL = 9
 OPT_KEEP_COUNTERS = 10
+OPT_SPLIT_HIT_PCT = 12
 
 
 def f32_array(values, n):
