@@ -84,9 +84,11 @@ typedef struct XnartFrame {
     int32_t maxReflections; /* RayTracer.MaxReflections, RayTracer.cs:33 */
     int32_t filtering;      /* XNART_FILTER_*  */
     int32_t addressMode;    /* XNART_ADDRESS_* */
-    int32_t semantics;      /* XNART_SEMANTICS_*: the Color(Vector3) pack (XNA 4.0 rounds half to even, MonoGame
-                               truncates).  The slab test on the device is always the XNA 4.0 reciprocal-multiply form,
-                               the one the reference links (RayTraceProject.csproj:65); XNART_OPT_SEMANTICS refuses MonoGame */
+    int32_t semantics;      /* XNART_SEMANTICS_*: which framework's arithmetic the frame follows where XNA 4.0 and MonoGame
+                               differ: the Color(Vector3) pack (round half to even / truncate) and
+                               BoundingBox.Intersects(Ray) (reciprocal-multiply / divide form).  XNA 4.0 is what the reference
+                               links (RayTraceProject.csproj:65) and what the fast kernels implement; MonoGame frames are
+                               rendered by one generic kernel (a compatibility mode) */
     /* Row sharding for multi-GPU (RayTracer.cs:49-52 treats scanlines as independent work
      * items): this call renders only scanline bands b with (b % shardCount) == shardIndex,
      * a band being shardBandRows consecutive scanlines.  shardCount <= 1 renders everything. */

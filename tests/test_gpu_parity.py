@@ -142,11 +142,11 @@ def test_depths_modes_and_shards(X, oracle_mod):
     assert x.kernel_launches() - n0 == 1
     assert np.array_equal(fused, per_level) and np.array_equal(fused, o.render_frame(f, n_threads=4))
     x.set_option(records.OPT_FUSE_FRAME, 0)
-    f = s.frame(160, 120, semantics=records.SEMANTICS_MONOGAME)  # colour pack by truncation
-    # (slab form stays XNA 4.0 on the device; the oracle's slab switch follows the frame, so compare packs only
-    # on this scene, whose single-leaf trees make the slab form irrelevant to the result)
+    f = s.frame(160, 120, semantics=records.SEMANTICS_MONOGAME)  # MonoGame: truncating colour pack, divide-form slab test
+    o.set_semantics(records.SEMANTICS_MONOGAME)
     got = x.render_frame(f)
-    assert (got != x.render_frame(s.frame(160, 120))).any()
+    assert np.array_equal(got, o.render_frame(f, n_threads=4)) and (got != x.render_frame(s.frame(160, 120))).any()
+    o.set_semantics(records.SEMANTICS_XNA40)
     full = x.render_frame(s.frame(160, 120)).copy()
     parts = np.zeros_like(full)
     for r in range(3):
@@ -522,14 +522,14 @@ def test_crate_at_baseline_sizes_equals_oracle(X, oracle_mod, wh):
     x.close()
 
 
-def test_monogame_pack_equals_oracle(X, oracle_mod):
-    """XnartFrame.semantics selects the Color(Vector3) pack; the slab test on the device is always the XNA 4.0 form
-    (include/xnart.h).  Against the oracle configured the same way — MonoGame's truncating pack, XNA 4.0 slab test —
-    every pixel agrees, on single-leaf trees (crate), a deep octree (grid) and the transparent default scene."""
-    for name, wh in (("crate", (320, 240)), ("grid", (240, 135)), ("spheres", (128, 128))):
+def test_monogame_semantics_equal_oracle(X, oracle_mod):
+    """XNART_SEMANTICS_MONOGAME = MonoGame's truncating Color pack AND its divide-form BoundingBox.Intersects (nullable
+    tMin / tMax, 0 only when the origin lies strictly between the planes: SURVEY.md F6 / A.1), on the device as in the
+    oracle: whole frames (single-leaf trees, a deep octree, the transparent default scene, a split scene octree) and
+    per-ray hits, including rays that start ON box faces, where the two frameworks disagree."""
+    for name, wh in (("crate", (320, 240)), ("grid", (240, 135)), ("spheres", (128, 128)), ("many", (160, 120))):
         s = make_scene(name)
-        o = oracle_mod.Oracle()
-        o.set_slab_override(records.SEMANTICS_XNA40)
+        o = oracle_mod.Oracle(semantics=records.SEMANTICS_MONOGAME)
         scenes.upload(o, s)
         x = X.Xnart()
         scenes.upload(x, s)
@@ -538,10 +538,36 @@ def test_monogame_pack_equals_oracle(X, oracle_mod):
         got = x.render_frame(f)
         assert np.array_equal(want, got), (name, int((want != got).sum()))
         assert (got != x.render_frame(s.frame(*wh))).any(), name
-        with pytest.raises(X.XnartError) as e:     # the MonoGame slab form is not offered on the device
-            x.set_option(records.OPT_SEMANTICS, records.SEMANTICS_MONOGAME)
-        assert e.value.code == records.XNART_ERR_UNSUPPORTED
+        oc, xc = o.counters(), x.counters()
+        for k in ("raysPrimary", "raysShadow", "raysReflection", "raysRefraction", "hits"):
+            assert getattr(oc, k) == getattr(xc, k), (name, k)
         x.close()
+    differ = 0
+    for name in ("crate", "soup", "grid"):
+        s = make_scene(name)
+        o = oracle_mod.Oracle(semantics=records.SEMANTICS_MONOGAME)
+        scenes.upload(o, s)
+        ox = oracle_mod.Oracle()
+        scenes.upload(ox, s)
+        x = X.Xnart()
+        scenes.upload(x, s)
+        x.set_option(records.OPT_SEMANTICS, records.SEMANTICS_MONOGAME)
+        rays = np.concatenate([oracle_mod.primary_rays(s.frame(96, 64)), random_rays(20000, 16.0, 11)])
+        want = o.trace_rays(rays)
+        assert_hits_identical(want, x.trace_rays(rays))
+        hit = want["tri"] >= 0
+        rng = np.random.default_rng(3)
+        d = rng.normal(size=want["pos"][hit].shape)
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        rays2 = np.concatenate([want["pos"][hit], d], axis=1).astype(np.float32)   # origins on triangles, i.e. on box faces
+        ign = np.stack([want["mesh"][hit], want["tri"][hit]], axis=1).astype(np.int32)
+        w2 = o.trace_rays(rays2, ign)
+        assert_hits_identical(w2, x.trace_rays(rays2, ign))
+        differ += int((w2["tri"] != ox.trace_rays(rays2, ign)["tri"]).sum()) + int((want["tri"] != ox.trace_rays(rays)["tri"]).sum())
+        x.set_option(records.OPT_SEMANTICS, records.SEMANTICS_XNA40)
+        assert_hits_identical(ox.trace_rays(rays2, ign), x.trace_rays(rays2, ign))
+        x.close()
+    assert differ > 100, "the ray sets no longer tell the two slab forms apart"
 
 
 def test_default_spheres_512_equals_oracle(X, oracle_mod):

@@ -40,7 +40,7 @@ namespace xn {
 // MINB = resident blocks per SM the register allocation is sized for: 2 (128 registers) suits
 // leaf-sized meshes where the kernel is issue bound; 4 (64 registers, some spilling) suits deep
 // octrees, where the walk is bound by dependent-load latency and more resident warps hide it.
-template <bool COUNT, bool LEAFONLY>
+template <bool COUNT, bool LEAFONLY, bool MONO = false>
 __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* __restrict__ lights,
                                           int level, Ctr& ctr, unsigned& nHits, unsigned& nRefl, unsigned& nRefr) {
     unsigned count, base;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, 
         int triG = 0;
         for (int q = 0;; q++) {
             Hit h;
-            bool ok = traceScene<COUNT, LEAFONLY>(S, qo, qd, qm, qt, h, ctr);
+            bool ok = traceScene<COUNT, LEAFONLY, MONO>(S, qo, qd, qm, qt, h, ctr);
             if (q == 0) {
                 if (!ok) break;
                 hit = true;
@@ -90,12 +90,14 @@ __device__ __forceinline__ void levelBody(const DevScene& S, const DevFrame& F, 
 
 // THREADS x MINB fixes the register budget (128 x 6 or 256 x 3 -> 80 registers, 128 x 5 -> 96, 256 x 2 -> 128, 256 x 4 -> 64).
 // Measured on the 1080p crate frame (levels, ms): 128x6 0.404, 256x3 0.417, 128x5 0.415, 128x4 0.418, 192x3 0.438.
-template <bool COUNT, int MINB, bool LEAFONLY, int THREADS = 256>
+// MONO: the MonoGame form of BoundingBox.Intersects (trace.cuh: slabMonoGame) everywhere a box is tested; one generic
+// build serves every scene (XnartFrame.semantics == XNART_SEMANTICS_MONOGAME is a compatibility mode, not a fast path).
+template <bool COUNT, int MINB, bool LEAFONLY, int THREADS = 256, bool MONO = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_level(DevScene S, DevFrame F, DevArena A, const DevLight* __restrict__ lights, int level) {
     Ctr ctr;
     ctr.nBox = ctr.nTriRef = ctr.nTriCulled = ctr.nTriFull = 0;
     unsigned nHits = 0, nRefl = 0, nRefr = 0;
-    levelBody<COUNT, LEAFONLY>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
+    levelBody<COUNT, LEAFONLY, MONO>(S, F, A, lights, level, ctr, nHits, nRefl, nRefr);
     flushCounters<COUNT>(A, ctr, nHits, nRefl, nRefr);
 }
 
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256) k_resolve_chain(DevFrame F, DevArena A, u
 }
 
 // Batch form of ISpatialManager.GetRayIntersection for parity tests (one thread per ray).
-template <bool COUNT>
+template <bool COUNT, bool MONO = false>
 __global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_trace_rays(DevScene S, const float* __restrict__ rays6, long long n,
                                                                          const int* __restrict__ ignore2, int* __restrict__ objId,
                                                                          int* __restrict__ meshId, int* __restrict__ triId,
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(256, XN_LEVEL_MIN_BLOCKS) k_trace_rays(DevScen
         if (ignore2) { im = ignore2[2 * i]; it = ignore2[2 * i + 1]; }
         Hit h;
         h.obj = h.mesh = h.tri = -1; h.key = 0; h.u = h.v = h.d = 0.0f; h.pos = mk(0.0f, 0.0f, 0.0f);
-        const bool ok = traceScene<COUNT>(S, ro, rd, im, it, h, ctr);
+        const bool ok = traceScene<COUNT, false, MONO>(S, ro, rd, im, it, h, ctr);
         if (ok) nHits++;
         objId[i] = ok ? h.obj : -1; meshId[i] = ok ? h.mesh : -1; triId[i] = ok ? h.tri : -1;
         u[i] = ok ? h.u : 0.0f; v[i] = ok ? h.v : 0.0f; d[i] = ok ? h.d : 0.0f;
@@ -250,7 +252,9 @@ static inline int gridFor(long long n, int maxBlocks) {
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
                         long long upperBound, int maxBlocks, bool count, int kind, cudaStream_t st) {
     int grid = gridFor(upperBound, maxBlocks);
-    if (kind == 2) {          // deep octrees: high-occupancy build
+    if (kind == 3) {          // MonoGame slab form: one generic build (the instrumented counters are those of the XNA 4.0 walk)
+        k_level<false, XN_LEVEL_MIN_BLOCKS, false, 256, true><<<grid, 256, 0, st>>>(S, F, A, lights, level);
+    } else if (kind == 2) {          // deep octrees: high-occupancy build
         if (count) k_level<true, XN_DEEP_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
         else k_level<false, XN_DEEP_MIN_BLOCKS, false><<<grid, 256, 0, st>>>(S, F, A, lights, level);
     } else if (kind == 1) {   // octrees with one split
@@ -296,9 +300,10 @@ cudaError_t launchResolve(const DevFrame& F, const DevArena& A, int level, long 
 
 cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
-                            int maxBlocks, bool count, cudaStream_t st) {
+                            int maxBlocks, bool count, bool mono, cudaStream_t st) {
     int grid = gridFor(n, maxBlocks);
-    if (count) k_trace_rays<true><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+    if (mono) k_trace_rays<false, true><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
+    else if (count) k_trace_rays<true><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
     else k_trace_rays<false><<<grid, 256, 0, st>>>(S, rays6, n, ignore2, objId, meshId, triId, u, v, d, pos3, counters);
     return cudaGetLastError();
 }

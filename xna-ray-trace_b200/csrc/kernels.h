@@ -10,7 +10,8 @@ namespace xn {
 
 // One wave of the trace loop: closest hit + shadow rays + shading for every ray of `level`.
 // upperBound only sizes the grid (the real count is read on the device).  kind: 0 = every MeshOctree is a
-// single leaf (build without expansion code), 1 = shallow octrees, 2 = deep octrees (64-register build).
+// single leaf (build without expansion code), 1 = shallow octrees, 2 = deep octrees (64-register build), 3 = any scene with the
+// MonoGame form of the slab test (XNART_SEMANTICS_MONOGAME).
 cudaError_t launchLevel(const DevScene& S, const DevFrame& F, const DevArena& A, const DevLight* lights, int level,
                         long long upperBound, int maxBlocks, bool count, int kind, cudaStream_t st);
 
@@ -30,7 +31,7 @@ cudaError_t launchResolveChain(const DevFrame& F, const DevArena& A, int maxBloc
 // Batch closest-hit queries (xnart_trace_rays).
 cudaError_t launchTraceRays(const DevScene& S, const float* rays6, long long n, const int* ignore2, int* objId, int* meshId,
                             int* triId, float* u, float* v, float* d, float* pos3, unsigned long long* counters,
-                            int maxBlocks, bool count, cudaStream_t st);
+                            int maxBlocks, bool count, bool mono, cudaStream_t st);
 
 // ---- small opaque scenes (path.cu): the whole frame in one persistent launch -----------------
 int pathKernelBlocksPerSm(bool count);

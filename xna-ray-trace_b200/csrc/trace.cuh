@@ -102,6 +102,45 @@ __device__ __forceinline__ bool slab(float3 mn, float3 mx, const RayPre& r, floa
     return slab2(mn, mx, r, t, tExit);
 }
 
+// BoundingBox.Intersects(ref Ray, out float?) — MonoGame form: divides by the direction instead of
+// multiplying by its reciprocal (different last-bit rounding, hence different groups of bit-equal entry distances),
+// nullable tMin / tMax set by the first non-parallel axis, per-axis rejection, and at the end: 0 when the origin lies
+// between the planes (tMin < 0 < tMax), null when the box lies behind (tMin < 0), tMin otherwise.
+__device__ __forceinline__ bool slabMonoGame(float3 mn, float3 mx, const RayPre& r, float& t) {
+    bool has = false;
+    float tMin = 0.0f, tMax = 0.0f;
+    const float lo[3] = {mn.x, mn.y, mn.z}, hi[3] = {mx.x, mx.y, mx.z};
+    const float p[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (fabsf(d[a]) < 1e-6f) {
+            if (p[a] < lo[a] || p[a] > hi[a]) return false;
+        } else {
+            float t1 = (lo[a] - p[a]) / d[a];
+            float t2 = (hi[a] - p[a]) / d[a];
+            if (t1 > t2) { const float s = t1; t1 = t2; t2 = s; }
+            if (!has) {
+                tMin = t1; tMax = t2; has = true;
+            } else {
+                if (tMin > t2 || t1 > tMax) return false;
+                if (t1 > tMin) tMin = t1;
+                if (t2 < tMax) tMax = t2;
+            }
+        }
+    }
+    if (!has) return false;                               // "return tMin" with tMin == null
+    if (tMin < 0.0f && tMax > 0.0f) { t = 0.0f; return true; }
+    if (tMin < 0.0f) return false;
+    t = tMin;
+    return true;
+}
+// The slab test of the framework the caller asked for (XnartFrame.semantics / XNART_OPT_SEMANTICS).
+template <bool MONO>
+__device__ __forceinline__ bool slabF(float3 mn, float3 mx, const RayPre& r, float& t) {
+    if (MONO) return slabMonoGame(mn, mx, r, t);
+    return slab(mn, mx, r, t);
+}
+
 // Vector3.Transform with the matrix fetched as four 16-byte rows (SceneObject.World / InverseWorld
 // live in global memory: 4 loads instead of 12).
 struct M43 { float4 r0, r1, r2, r3; };
@@ -118,11 +157,12 @@ __device__ __forceinline__ V3 transform43(V3 p, const M43& m) {
 }
 
 // Mesh.RayIntersects (Mesh.cs:34-39): slab test on Mesh.MeshBoundingBox (bytes 0..23 of DevMesh).
+template <bool MONO = false>
 __device__ __forceinline__ bool meshBoxSlab(const DevMesh* __restrict__ M, const RayPre& r) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(M->box));
     const float2 b1 = __ldg(reinterpret_cast<const float2*>(M->box + 4));
     float tb;
-    return slab(make_float3(b0.x, b0.y, b0.z), make_float3(b0.w, b1.x, b1.y), r, tb);
+    return slabF<MONO>(make_float3(b0.x, b0.y, b0.z), make_float3(b0.w, b1.x, b1.y), r, tb);
 }
 
 struct MeshHit {
@@ -211,14 +251,18 @@ struct Seg {
     float aLo, bHi;   // node filter: skip when exit < aLo or entry >= bHi
 };
 
-template <bool COUNT>
+template <bool COUNT, bool MONO = false>
 __device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const RayPre& r, Walk& w, Ctr& ctr, float* tExitOut = nullptr) {
-    float t0, t1;
+    float t0, t1 = 0.0f;
     if (COUNT) ctr.nBox++;
     // rootBox[0..5], rootA, rootB = bytes 24..55 of DevMesh
     const float2 rb0 = __ldg(reinterpret_cast<const float2*>(M->rootBox));
     const float4 rb1 = __ldg(reinterpret_cast<const float4*>(M->rootBox + 2));
-    if (!slab2(make_float3(rb0.x, rb0.y, rb1.x), make_float3(rb1.y, rb1.z, rb1.w), r, t0, t1)) return false;
+    if (MONO) {
+        if (!slabMonoGame(make_float3(rb0.x, rb0.y, rb1.x), make_float3(rb1.y, rb1.z, rb1.w), r, t0)) return false;
+    } else {
+        if (!slab2(make_float3(rb0.x, rb0.y, rb1.x), make_float3(rb1.y, rb1.z, rb1.w), r, t0, t1)) return false;
+    }
     if (tExitOut) *tExitOut = t1;
     const int2 rd = __ldg(reinterpret_cast<const int2*>(&M->rootA));
     w.K = INFINITY; w.bd = w.bu = w.bv = 0.0f; w.btri = -1; w.bkey = 0;
@@ -227,7 +271,7 @@ __device__ __forceinline__ bool walkStart(const DevMesh* __restrict__ M, const R
 }
 
 // Returns true when the walk is over (nothing held, stack empty).
-template <bool COUNT, int STEPS = XN_DESCEND_MAX, bool SEG = false>
+template <bool COUNT, int STEPS = XN_DESCEND_MAX, bool SEG = false, bool MONO = false>
 __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, Walk& w, WalkEntry* __restrict__ stack, Ctr& ctr,
                                             const Seg& seg = Seg()) {
     const bool ox = (r.oct & 4) != 0, oy = (r.oct & 2) != 0, oz = (r.oct & 1) != 0;
@@ -270,12 +314,12 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
             // entered after K: prune on the conservative box (own Min, consMax)
             const float4 qc = Rzc.b;
             float tcns;
-            bool h = slab(make_float3(qx.x, qy.x, qz.x), make_float3(qc.x, qc.y, qc.z), r, tcns);
+            bool h = slabF<MONO>(make_float3(qx.x, qy.x, qz.x), make_float3(qc.x, qc.y, qc.z), r, tcns);
             if (h && tcns > w.K) { w.have = false; continue; }
         }
         if (COUNT) ctr.nBox += 8;
         w.have = false;
-        if (r.par == 0) {
+        if (!MONO && r.par == 0) {
             // planes in the order the ray meets them: (lo0, hi0, lo1, hi1), reversed for a negative
             // direction; (plane - origin) * inv is monotone in the plane, so near/far need no compare
             const float x0 = ((ox ? qx.w : qx.x) - r.o.x) * r.inv.x, x1 = ((ox ? qx.z : qx.y) - r.o.x) * r.inv.x;
@@ -312,8 +356,8 @@ __device__ __forceinline__ bool walkDescend(const DevScene& S, const RayPre& r, 
                 const int c = p ^ r.oct;
                 const int i = c >> 2, j = (c >> 1) & 1, k = c & 1;
                 float tc;
-                const bool h = slab(make_float3(i ? lx[1] : lx[0], j ? ly[1] : ly[0], k ? lz[1] : lz[0]),
-                                    make_float3(i ? hx[1] : hx[0], j ? hy[1] : hy[0], k ? hz[1] : hz[0]), r, tc);
+                const bool h = slabF<MONO>(make_float3(i ? lx[1] : lx[0], j ? ly[1] : ly[0], k ? lz[1] : lz[0]),
+                                           make_float3(i ? hx[1] : hx[0], j ? hy[1] : hy[0], k ? hz[1] : hz[0]), r, tc);
                 const int2 d = ds[p];
                 // (segments: the containment branch has no exit distance at hand; internal nodes are kept)
                 bool take = h && d.y != 0 && (d.y < 0 || !(tc > w.K));
@@ -454,17 +498,17 @@ __device__ __forceinline__ void walkLeafWarp(const DevScene& S, int src, const R
 // One thread, one ray: the whole walk.  LEAFONLY: every MeshOctree of the scene is a single leaf
 // (<= itemTreshold triangles per mesh, e.g. the Free_crate scene) — the expansion code and the stack
 // are compiled out, which is worth a third of the registers of the level kernel.
-template <bool COUNT, bool LEAFONLY>
+template <bool COUNT, bool LEAFONLY, bool MONO = false>
 __device__ __forceinline__ bool traceMesh(const DevScene& S, const DevMesh* __restrict__ M, const RayPre& r, int ignoreTri,
                                           MeshHit& out, Ctr& ctr) {
     Walk w;
-    if (!walkStart<COUNT>(M, r, w, ctr)) return false;
+    if (!walkStart<COUNT, MONO>(M, r, w, ctr)) return false;
     if (LEAFONLY) {
         while (w.have) walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
     } else {
         WalkEntry stack[kMeshStack];
         for (;;) {
-            if (walkDescend<COUNT>(S, r, w, stack, ctr)) break;
+            if (walkDescend<COUNT, XN_DESCEND_MAX, false, MONO>(S, r, w, stack, ctr)) break;
             walkLeaf<COUNT>(S, r, ignoreTri, w, ctr);
         }
     }
@@ -483,7 +527,7 @@ struct Hit {
 // The object-space ray depends on the object through InverseWorld only, so objects whose matrices are
 // bit-identical (DevObj.xformClass: e.g. every object placed with the identity) share it: `cls`/`r`/`rOk`
 // carry the ray of the class seen last from one call to the next.
-template <bool COUNT, bool LEAFONLY>
+template <bool COUNT, bool LEAFONLY, bool MONO = false>
 __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro, V3 rd, int ignMesh, int ignTri,
                                             float& minDistance, bool& found, Hit& best, Ctr& ctr, int& cls, RayPre& r, bool& rOk) {
     const DevObj* __restrict__ O = &S.objs[objIdx];
@@ -505,10 +549,10 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
         int meshId = __ldg(&S.objMeshIds[ms + mi]);
         const DevMesh* __restrict__ M = &S.meshes[meshId];
         if (COUNT) ctr.nBox++;
-        if (!meshBoxSlab(M, r)) continue;
+        if (!meshBoxSlab<MONO>(M, r)) continue;
         MeshHit mh;
         int ign = (ignMesh == meshId) ? ignTri : -1;
-        const bool ok = traceMesh<COUNT, LEAFONLY>(S, M, r, ign, mh, ctr);
+        const bool ok = traceMesh<COUNT, LEAFONLY, MONO>(S, M, r, ign, mh, ctr);
         if (ok && mh.d < minDistance) {
             minDistance = mh.d;
             best.obj = objIdx; best.mesh = meshId; best.tri = mh.tri; best.key = mh.key;
@@ -522,7 +566,7 @@ __device__ __forceinline__ void objectQuery(const DevScene& S, int objIdx, V3 ro
 // OctreeSpatialManager.GetRayIntersection.  Same group/early-exit semantics one level up; with
 // <= itemTreshold (20) objects the tree is the root leaf alone.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT, bool LEAFONLY = false>
+template <bool COUNT, bool LEAFONLY = false, bool MONO = false>
 __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int ignMesh, int ignTri, Hit& out, Ctr& ctr) {
     if (!finite3(ro) || !finite3(rd)) return false;
     const bool cnt = COUNT;
@@ -531,7 +575,7 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
     float4 lo = __ldg(&nodes[2 * S.sceneRoot]), hi = __ldg(&nodes[2 * S.sceneRoot + 1]);
     float t0;
     if (cnt) ctr.nBox++;
-    if (!slab(make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z), r, t0)) return false;
+    if (!slabF<MONO>(make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z), r, t0)) return false;
     int w0 = __float_as_int(lo.w), w1 = __float_as_int(hi.w);
     bool found = false;
     Hit best;
@@ -558,7 +602,7 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
             for (int i = 0; i < w1; i++) {
                 const float before = ld;
                 const bool fb = lf;
-                objectQuery<COUNT, LEAFONLY>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr, cls, ro_, roOk);
+                objectQuery<COUNT, LEAFONLY, MONO>(S, __ldg(&S.refs[w0 + i]), ro, rd, ignMesh, ignTri, ld, lf, lh, ctr, cls, ro_, roOk);
                 if (lf && (!fb || ld < before)) lkey = w0 + i;
             }
             if (lf) {
@@ -574,7 +618,7 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
                 float4 clo = __ldg(&nodes[2 * c]), chi = __ldg(&nodes[2 * c + 1]);
                 float tc;
                 if (cnt) ctr.nBox++;
-                if (slab(make_float3(clo.x, clo.y, clo.z), make_float3(chi.x, chi.y, chi.z), r, tc)) {
+                if (slabF<MONO>(make_float3(clo.x, clo.y, clo.z), make_float3(chi.x, chi.y, chi.z), r, tc)) {
                     if (!(tc > K) || __float_as_int(chi.w) < 0) { stack[sp].node = c; stack[sp].t = tc; sp++; }
                 }
             }
@@ -590,7 +634,7 @@ __device__ __forceinline__ bool traceScene(const DevScene& S, V3 ro, V3 rd, int 
                 if (nw1 >= 0) continue;
                 float4 cm = __ldg(&S.consMax[-1 - nw1]);
                 float tcns;
-                bool h = slab(make_float3(nlo.x, nlo.y, nlo.z), make_float3(cm.x, cm.y, cm.z), r, tcns);
+                bool h = slabF<MONO>(make_float3(nlo.x, nlo.y, nlo.z), make_float3(cm.x, cm.y, cm.z), r, tcns);
                 if (h && tcns > K) continue;
             }
             w0 = __float_as_int(nlo.w); w1 = nw1; tcur = tn;

@@ -243,7 +243,7 @@ int32_t xnart_set_option(XnartCtx* c, int32_t option, int64_t value) {
             if (value < (1 << 20)) return fail(c, XNART_ERR_INVALID_ARGUMENT, "arena limit too small");
             c->arenaLimit = value; return XNART_OK;
         case XNART_OPT_SEMANTICS:
-            if (value != XNART_SEMANTICS_XNA40) return fail(c, XNART_ERR_UNSUPPORTED, "only XNA 4.0 slab semantics are implemented on the device");
+            if (value != XNART_SEMANTICS_XNA40 && value != XNART_SEMANTICS_MONOGAME) return fail(c, XNART_ERR_INVALID_ARGUMENT, "unknown semantics");
             c->traceSemantics = (int)value; return XNART_OK;
         case XNART_OPT_FUSE_FRAME: c->fuseFrame = value != 0; return XNART_OK;
         case XNART_OPT_OVERLAP_LEVELS: c->overlapLevels = value != 0; return XNART_OK;
@@ -771,7 +771,8 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     d.lastPixels = accumulate ? d.lastPixels + localPixels : localPixels;
     d.lastLights = F.nLights;
     d.progressEnqueued += (unsigned long long)localPixels;
-    if (usePath(c, d)) {
+    const bool mono = f.semantics == XNART_SEMANTICS_MONOGAME;   // compatibility mode: the generic level kernel, MonoGame slab form
+    if (!mono && usePath(c, d)) {
         if (localPixels > 0x7fffffffLL) return fail(c, XNART_ERR_UNSUPPORTED, "too many pixels in one shard");
         // no arena, no chunks: one persistent launch renders the shard (path.cu)
         F.pixelBase = 0;
@@ -796,7 +797,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     // transparent material can fork every hit into reflection + refraction (RayTracer.cs:586-702)
     const double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
     const double raysPerPixel = c->hasTransparent ? std::ldexp(1.0, D) : 1.0;
-    const bool wave = useWave(c, d);
+    const bool wave = !mono && useWave(c, d);
     const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * (80.0 + (wave ? 2.0 * (32.0 + 72.0 * std::max(F.nLights, 1)) : 0.0)) + 64.0;
     long long chunk = (long long)std::floor((double)c->arenaLimit / bytesPerPixel);
     chunk = std::min<long long>(chunk, (long long)(4.0e9 / nodesPerPixel));
@@ -819,7 +820,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     // Shallow scenes (every MeshOctree a leaf or one split): launch overhead of the deep, nearly
     // empty levels matters -> one cooperative launch per chunk.  Deep scenes keep one launch per
     // level in the high-occupancy build of the kernel.
-    const bool fused = !wave && c->fuseFrame && !deepScene(c) && d.frameBlocks > 0 && d.frameBlocksCount > 0;
+    const bool fused = !mono && !wave && c->fuseFrame && !deepScene(c) && d.frameBlocks > 0 && d.frameBlocksCount > 0;
     d.lastFused = fused;
     d.lastWave = wave;
 
@@ -842,7 +843,7 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
                 // deep levels usually hold a small fraction of the rays: a grid of resident blocks only (the
                 // kernels are grid-stride loops) keeps the cost of a nearly empty launch down
                 const int cap = (L >= 2 && !c->hasTransparent) ? d.smCount * 3 : maxBlocks;
-                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, cap, c->countKernels, deepScene(c) ? 2 : (c->maxMeshDepth >= 1 ? 1 : 0), st));
+                CU_TRY(c, launchLevel(d.scene, F, d.arena, d.lights, L, (long long)ub, cap, c->countKernels, mono ? 3 : (deepScene(c) ? 2 : (c->maxMeshDepth >= 1 ? 1 : 0)), st));
                 c->launches++;
                 continue;
             }
@@ -988,7 +989,7 @@ int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* de
     const int sc = frame->shardCount > 1 ? frame->shardCount : 1;
     const int si = sc > 1 ? frame->shardIndex : 0, br = sc > 1 ? frame->shardBandRows : 8;
     const int k = (int)states.size();
-    const bool sub = k > 1 && useWave(c, d) && (long long)br * sc * k <= (long long)frame->vpH;
+    const bool sub = k > 1 && frame->semantics != XNART_SEMANTICS_MONOGAME && useWave(c, d) && (long long)br * sc * k <= (long long)frame->vpH;
     auto enqueueAll = [&]() -> int {
         if (!sub) return enqueueFrame(c, d, *frame, (uint32_t*)devOut, st);
         CU_TRY(c, cudaEventRecord(d.evRendered[0], st));
@@ -1344,7 +1345,8 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
     CU_TRY(c, cudaSetDevice(d.dev));
     size_t N = (size_t)n;
     if (N > 0x7fffffffULL) return fail(c, XNART_ERR_UNSUPPORTED, "xnart_trace_rays: too many rays in one batch");
-    const bool wave = useWave(c, d);
+    const bool monoT = c->traceSemantics == XNART_SEMANTICS_MONOGAME;
+    const bool wave = !monoT && useWave(c, d);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t need = al(N * 24) + 6 * al(N * 4) + al(N * 12) + al(N * 8);
     if (wave) need += 2 * al(N * 16) + al(N * 8) + al(N * 32) + 256;
@@ -1376,7 +1378,7 @@ int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32
         TR_TRY(launchUnpackHits(d.scene, qh, n, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, d.stream));
         c->launches += 3;
     } else {
-        TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, d.stream));
+        TR_TRY(launchTraceRays(d.scene, dr, n, di, dobj, dmesh, dtri, du, dv, dd, dp, d.counters, d.smCount * 8, c->countKernels, monoT, d.stream));
         c->launches++;
     }
     TR_TRY(cudaMemcpyAsync(objId, dobj, N * 4, cudaMemcpyDeviceToHost, d.stream));
