@@ -2,10 +2,10 @@
 """bench.py — headline measurement of the trace path (BASELINE.json: Mrays/s, frames/s at 1080p).
 
 Own arm (default):   python bench.py --gpus N --steps K --warmup W
-    step   = every rank renders --frames-per-step (64) 1920x1080 frames of the Free_crate scene (configs[1]:
+    step   = every rank renders --frames-per-step (128) 1920x1080 frames of the Free_crate scene (configs[1]:
              depth 8, Point+Wrap, 1 spot light), each from its own orbit camera — frames of a flythrough are
              the path's natural multi-GPU axis (weak scaling) — and ships them to rank 0 over NVLink.
-             Scene resident on the GPU, output stays on the device.  20 steps = 1280 frames per GPU.
+             Scene resident on the GPU, output stays on the device.  20 steps = 2560 frames per GPU, about half a second of device time.
     value  = rays traced by all ranks / device time (CUDA events on the launching stream, max over ranks), Mrays/s
     e2e    = same metric through the reference-facing C-ABI call xnart_render_frames with HOST buffers: the
              XnartFrame records go in, the finished frames come back to page-locked host memory inside the
@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xnart", choices=["xnart", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=64, help="1080p frames every GPU renders per step")
+    ap.add_argument("--frames-per-step", type=int, default=128, help="1080p frames every GPU renders per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-deep-scene", action="store_true", help="skip the 1M-triangle measurement at N=1")
     ap.add_argument("--extras", default="tile_split_4k,flythrough_1M,soup_10M",

@@ -727,3 +727,66 @@ def test_sub_shards_over_in_flight_states(X, oracle_mod):
     assert np.array_equal(o.render_frame(f, n_threads=8), b.cpu().numpy().view(np.uint32))
     x1.close()
     x3.close()
+
+
+def test_frames_to_dib24_equals_host_conversion(X):
+    """xnart_frames_to_dib24 (VideoStream.AddFrame's RotateNoneFlipY + LockBits as 24bpp, VideoStream.cs:344-365) writes
+    the bytes avi.to_dib_bits produces on the host — for widths with and without row padding and unaligned rows."""
+    import torch
+
+    from xna_ray_trace_b200 import avi
+
+    rng = np.random.default_rng(5)
+    for w, h, n in ((64, 8, 3), (101, 7, 2), (6, 5, 1), (1920, 16, 2), (3, 2, 4)):
+        frames = rng.integers(0, 2 ** 32, size=(n, h, w), dtype=np.uint64).astype(np.uint32)
+        stride = (3 * w + 3) & ~3
+        src = torch.from_numpy(frames.view(np.int32)).cuda()
+        dst = torch.full((n, h * stride), 0x55, dtype=torch.uint8, device="cuda:0")
+        X.frames_to_dib24(0, src.data_ptr(), n, w, h, stride, dst.data_ptr())
+        torch.cuda.synchronize()
+        got = dst.cpu().numpy()
+        for k in range(n):
+            bits, st = avi.to_dib_bits(frames[k], 24)
+            assert st == stride and bytes(got[k]) == bytes(bits), (w, h, k)
+
+
+def test_keep_counters_and_split_rule(X):
+    """XNART_OPT_KEEP_COUNTERS: statistics accumulate over render calls (exact ray totals of a flythrough).
+    XNART_OPT_SPLIT_HIT_PCT / XNART_OPT_SPLIT_RAYS only choose how a batch is scheduled: frames do not change."""
+    s = make_scene("grid")
+    x = X.Xnart()
+    x.set_option(records.OPT_TRAVERSAL, 2)
+    scenes.upload(x, s)
+    fa, fb = s.frame(160, 96), s.frame(200, 120)
+    a = x.render_frame(fa).copy()
+    ra = x.counters().rays
+    x.render_frame(fb)
+    rb = x.counters().rays
+    x.set_option(records.OPT_KEEP_COUNTERS, 1)
+    x.render_frame(fa); x.render_frame(fb); x.render_frames([fa, fa])
+    c = x.counters()
+    assert c.rays == 3 * ra + rb and c.pixels == 3 * 160 * 96 + 200 * 120
+    x.set_option(records.OPT_KEEP_COUNTERS, 0)
+    x.render_frame(fa)
+    assert x.counters().rays == ra
+    for pct in (0, 30, 100):
+        for split in (1 << 24, 5000):
+            x.set_option(records.OPT_SPLIT_HIT_PCT, pct)
+            x.set_option(records.OPT_SPLIT_RAYS, split)
+            assert np.array_equal(a, x.render_frame(fa)), (pct, split)
+    x.close()
+
+
+def test_measured_peaks_are_plausible(X):
+    """xnart_measure_peak (the roofline denominators bench.py reports): un-fused FP32 within 60-105 % of SMs x 128 lanes x
+    clock, and the memory hierarchy ordered L1 > L2 > HBM."""
+    import torch
+
+    p = torch.cuda.get_device_properties(0)
+    nominal = p.multi_processor_count * 128 * 1.965e9
+    fp32 = X.measure_peak(0, X.PEAK_FP32_NOFMA, reps=2)
+    l1, l2, hbm = (X.measure_peak(0, k, reps=2) for k in (X.PEAK_L1_READ, X.PEAK_L2_READ, X.PEAK_HBM_READ))
+    assert 0.6 * nominal < fp32 < 1.05 * nominal, fp32
+    assert l1 > l2 > hbm > 2e12, (l1, l2, hbm)
+    with pytest.raises(X.XnartError):
+        X.measure_peak(0, 9)
