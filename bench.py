@@ -387,12 +387,16 @@ def main():
         sums = [int(g[r, 0].to(torch.int64).bitwise_and(0xFFFFFF).sum().item()) for r in range(world)]
         gather_ok = all(v > 0 for v in sums) and len(set(sums)) == world
         del g
+    # the frames the timed region left behind (its last step) must be the frames an untimed render of that step gives
+    last_half = (warm + args.steps - 1) & 1
+    timed_sum = int(ring[last_half].to(torch.int64).bitwise_and(0xFFFFFF).sum().item())
     # rays of the timed steps: exact device counters of an untimed re-render of the same frames
     my_rays = 0.0
     for s in range(args.steps):
-        x.render_frames_device(step_frames[warm + s], ring[0].data_ptr(), None)
+        x.render_frames_device(step_frames[warm + s], ring[last_half ^ 1].data_ptr(), None)
         my_rays += float(x.counters().rays)
-    checksum = int(ring[0].to(torch.int64).bitwise_and(0xFFFFFF).sum().item())
+    checksum = int(ring[last_half ^ 1].to(torch.int64).bitwise_and(0xFFFFFF).sum().item())
+    frames_verified = checksum == timed_sum and len(torch.unique(ring[last_half][0])) > 1000
     t = torch.tensor([my_ms, my_rays], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -590,7 +594,7 @@ def main():
                     "cpus_bound_near_gpu": numa, "cpu_cores": os.cpu_count()},
             "frames_per_s": world * FPS * args.steps / (ms * 1e-3),
             "rays_per_frame": total_rays / (world * FPS * max(1, args.steps)),
-            "checksum": checksum,
+            "checksum": checksum, "timed_frames_match_rerender": bool(frames_verified),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 184 * FPS, "d2h_bytes_per_step": W * H * 4 * FPS,
                     "frames_per_s": world * FPS * args.steps / e2e_s, "checksum": e2e_checksum,
                     "api": "xnart_render_frames (one call per step: %d frames, %d in flight per GPU, page-locked host frames)" % (FPS, INFLIGHT),

@@ -1185,6 +1185,7 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
         uint32_t* buf = slot ? d.frameBuf2 : d.frameBuf;
         if (perDev[di] >= 2) {
             if (!outPinned && (rc = drain((size_t)nDev)) != XNART_OK) return rc;  // the staging slot must be free again
+            CU_TRY(c, cudaSetDevice(d.dev));                                       // (drain visits other devices)
             CU_TRY(c, cudaStreamWaitEvent(d.stream, d.evCopied[slot], 0));        // buffer free once its copy is done
         }
         rc = enqueueFrame(c, d, frames[f], buf, d.stream, /*accumulate=*/true);
