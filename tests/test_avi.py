@@ -95,3 +95,29 @@ def test_opendml_segments(tmp_path):
         pos += 8 + struct.unpack("<I", raw[pos + 4:pos + 8])[0]
         n += 1
     assert pos == len(raw) and n == len(r.Segments)
+
+
+def test_threaded_payload_writes_give_the_same_file(tmp_path):
+    """AviManager(io_threads=n): payloads written by worker threads at their reserved offsets; the file is byte for byte
+    the one the sequential writer produces, across RIFF segment boundaries (AVIX) and odd payload sizes."""
+    rng = np.random.default_rng(2)
+    frames = [rng.integers(0, 2 ** 32, size=(9, 13), dtype=np.uint64).astype(np.uint32) for _ in range(40)]
+    paths = []
+    for threads in (0, 3):
+        p = str(tmp_path / ("t%d.avi" % threads))
+        m = avi.AviManager(p, False, first_segment_limit=4000, segment_limit=3000, io_threads=threads)
+        s = m.AddVideoStream(False, 30, 0, 13, 9, avi.PIXELFORMAT_24BPP_RGB)
+        for k, f in enumerate(frames):
+            if k % 2:
+                bits, _ = avi.to_dib_bits(f, 24)
+                s.AddFrameBits(bits)
+            else:
+                s.AddFrame(f)
+            if k == 17:
+                s.Flush()
+        m.Close()
+        paths.append(p)
+    a, b = open(paths[0], "rb").read(), open(paths[1], "rb").read()
+    assert a == b and len(a) > 40 * 9 * 40
+    v = avi.AviManager(paths[1], True).GetVideoStream()
+    assert v.CountFrames == 40 and np.array_equal(v.GetBitmap(33) & 0xFFFFFF, frames[33] & 0xFFFFFF)

@@ -135,6 +135,10 @@ class VideoStream:
         self._m._write_frame(bits)
         self.CountFrames += 1
 
+    def Flush(self):
+        """Wait until every frame handed to AddFrame / AddFrameBits so far has reached the file (io_threads > 0)."""
+        self._m._flush_payloads()
+
     def GetBitmap(self, position):
         """Frame `position` as an (H, W) uint32 array in the XNA Color layout (files of this module)."""
         if self._reader is None:
@@ -152,11 +156,19 @@ class VideoStream:
 class AviManager:
     """aviFileWrapper_src/AviManager.cs: `AviManager(fileName, open)`; open=False creates/overwrites."""
 
-    def __init__(self, fileName, open_existing, first_segment_limit=FIRST_SEGMENT_LIMIT, segment_limit=SEGMENT_LIMIT):
+    def __init__(self, fileName, open_existing, first_segment_limit=FIRST_SEGMENT_LIMIT, segment_limit=SEGMENT_LIMIT, io_threads=0):
+        """io_threads > 0: frame payloads are written by that many worker threads (os.pwrite at the offset the frame was
+        given; the chunk headers and indexes stay sequential) — appending 3.7 GB of frames is otherwise one memcpy stream.
+        The caller must keep a frame's buffer alive until VideoStream.Flush() / Close()."""
         self.fileName = fileName
         self._open = bool(open_existing)
         self._stream = None
         self._f = None
+        self._pool, self._pending = None, []
+        if io_threads > 0 and not open_existing:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(max_workers=int(io_threads))
         self._limits = (int(first_segment_limit), int(segment_limit))
         if self._open:
             if not os.path.exists(fileName):
@@ -261,17 +273,33 @@ class AviManager:
             self._end_segment(last=False)
         pos = f.tell()
         f.write(_fourcc("00db") + struct.pack("<I", len(bits)))
-        f.write(bits)
+        if self._pool is None:
+            f.write(bits)
+        else:
+            # leave a hole of the payload's size and let a worker fill it
+            f.seek(pos + 8 + len(bits))
+            self._pending.append(self._pool.submit(os.pwrite, f.fileno(), bits, pos + 8))
         if len(bits) & 1:
             f.write(b"\0")
         self._seg_entries.append((pos + 8, len(bits)))
         if self._riff_start == 0:
             self._idx1.append((pos - (self._movi_start + 8), len(bits)))
 
+    def _flush_payloads(self):
+        pending, self._pending = self._pending, []
+        for fut in pending:
+            n = fut.result()          # re-raises a failed write (disk full ...)
+            if n is not None and n <= 0:
+                raise IOError("Exception in VideoStreamWrite: short write")
+
     def Close(self):
         """AviManager.Close (AviManager.cs:327): finishes the headers and indexes."""
         if self._f is None:
             return
+        self._flush_payloads()
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         if self._stream is not None:
             s, f = self._stream, self._f
             self._end_segment(last=True)

@@ -114,6 +114,8 @@ def render_flythrough(x, scene, cameras, width, height, sink=None, world=1, rank
                                     sink.AddFrameBits(host[q, k])
                                 else:
                                     sink.AddFrame(host[q, k].view(np.uint32))
+                    if hasattr(sink, "Flush"):
+                        sink.Flush()   # payload writers (AviManager io_threads) are done with this staging buffer
                     busy[0] += time.perf_counter() - tw
                 except Exception as e:   # e.g. disk full: keep draining so the render loop never blocks
                     failure.append(e)
