@@ -473,9 +473,16 @@ def test_path_kernel_is_one_launch_and_equals_level_kernels(X):
     scenes.upload(x, s)
     f = s.frame(1920, 1080)
     x.set_option(records.OPT_COUNTERS, 1)
+    import torch
+
+    dev = torch.zeros((1080, 1920), dtype=torch.int32, device="cuda:0")
+    n0 = x.kernel_launches()
+    x.render_frame_device(f, dev.data_ptr())
+    assert x.kernel_launches() - n0 == 1          # the whole frame: one launch
     n0 = x.kernel_launches()
     a = x.render_frame(f).copy()
-    assert x.kernel_launches() - n0 == 1
+    assert x.kernel_launches() - n0 <= 4          # host output: a few slices, each copied while the next one renders
+    assert np.array_equal(a, dev.cpu().numpy().view(np.uint32))
     ca = x.counters()
     x.set_option(records.OPT_PATH_KERNEL, 0)
     n0 = x.kernel_launches()

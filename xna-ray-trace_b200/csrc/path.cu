@@ -187,11 +187,11 @@ __device__ __forceinline__ void pixelOf32(const DevFrame& F, unsigned q, int& x,
 __device__ __forceinline__ void primaryRay(const DevFrame& F, unsigned idx, V3& o, V3& d) {
     float sx, sy;
     if (F.samples) {   // GetColorForQuadrant's sub-pixel positions (RayTracer.cs:220-232)
-        const float2 sp = F.samples[idx];
+        const float2 sp = F.samples[(unsigned long long)F.pixelBase + idx];
         sx = sp.x; sy = sp.y;
     } else {
         int x, y;
-        pixelOf32(F, idx, x, y);
+        pixelOf32(F, (unsigned)F.pixelBase + idx, x, y);
         sx = (float)x; sy = (float)y;
     }
     o = unproject(F, sx, sy, 0.0f);
@@ -249,7 +249,7 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
                         b = atomicAdd(fetch, (unsigned)XN_PATH_BATCH);
                         // RayTracer.Progress (RayTracer.cs:43-46): pixels handed out so far, for xnart_progress
                         if (F.progress && (b & (64u * XN_PATH_BATCH - 1u)) == 0u)
-                            *reinterpret_cast<volatile unsigned long long*>(F.progress) = F.progressBase + (b < total ? b : total);
+                            *reinterpret_cast<volatile unsigned long long*>(F.progress) = F.progressBase + (unsigned long long)F.pixelBase + (b < total ? b : total);
                     }
                     b = __shfl_sync(FULL, b, 0);
                     if (b >= total) { exhausted = true; break; }
@@ -328,7 +328,7 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
                 col = packColor(cv, F.semantics);
             }
             int x, y;
-            pixelOf32(F, (unsigned)pix, x, y);
+            pixelOf32(F, (unsigned)F.pixelBase + (unsigned)pix, x, y);
             out[(size_t)y * (size_t)F.vpW + (size_t)x] = col;   // renderTargetData[y*W + x] (:425)
             pix = -1;
             ro = mk(0.0f, 0.0f, 0.0f); rd = mk(0.48f, 0.6f, 0.64f);

@@ -742,8 +742,12 @@ static int validateFrame(XnartCtx* c, const XnartFrame* f) {
 }
 
 // Enqueue the whole trace loop of one frame shard on `st`, writing full-frame-indexed RGBA8 to devOut.
+// hostDst != NULL (page-locked, full-frame indexed like devOut): a frame rendered by the path kernel is cut into a few
+// slices of whole tile rows, and each slice is copied to the host on the state's copy stream while the next one renders
+// (the caller waits for copyStream); *sliced reports whether that happened — otherwise the caller copies the frame itself.
 static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32_t* devOut, cudaStream_t st, bool accumulate = false,
-                        const float2* devSamples = nullptr, long long nSamples = 0) {
+                        const float2* devSamples = nullptr, long long nSamples = 0, uint32_t* hostDst = nullptr, bool* sliced = nullptr) {
+    if (sliced) *sliced = false;
     const bool timeIt = !accumulate;          // a single render: per-stage events
     accumulate = accumulate || c->keepCounters;
     DevFrame F;
@@ -775,17 +779,32 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     if (!mono && usePath(c, d)) {
         if (localPixels > 0x7fffffffLL) return fail(c, XNART_ERR_UNSUPPORTED, "too many pixels in one shard");
         // no arena, no chunks: one persistent launch renders the shard (path.cu)
-        F.pixelBase = 0;
-        F.chunkPixels = (int)localPixels;
         F.tiled = (!devSamples && (f.vpW % 8 == 0) && (localPixels % (4LL * f.vpW) == 0)) ? 1 : 0;
         d.singleChunk = true; d.lastFused = false; d.lastWave = false; d.lastPath = true;
         if (!accumulate) CU_TRY(c, cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * kCounterSlots, st));
         if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[0], st));
-        CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * kLevelWords, st));
         unsigned* fetch = d.levelWords + 3 * (kMaxLevels + 2) + 2;
-        CU_TRY(c, launchPath(c->small, d.scene, F, d.lights, devOut, fetch, d.counters,
-                             c->countKernels ? d.pathBlocksCount : d.pathBlocks, c->countKernels, st));
-        c->launches++;
+        // slices of whole tile rows for the copy overlap (unsharded frames only: a slice is then a run of scanlines)
+        const long long tileRow = 4LL * f.vpW;
+        const long long tileRows = F.tiled ? localPixels / tileRow : 0;
+        int nSlices = 1;
+        if (hostDst && F.tiled && F.shardCount == 1 && localPixels >= (1 << 19) && tileRows >= 8) nSlices = 4;
+        for (int sIdx = 0; sIdx < nSlices; sIdx++) {
+            const long long r0 = tileRows * sIdx / nSlices, r1 = tileRows * (sIdx + 1) / nSlices;
+            F.pixelBase = nSlices > 1 ? r0 * tileRow : 0;
+            F.chunkPixels = (int)(nSlices > 1 ? (r1 - r0) * tileRow : localPixels);
+            CU_TRY(c, cudaMemsetAsync(d.levelWords, 0, sizeof(unsigned) * kLevelWords, st));
+            CU_TRY(c, launchPath(c->small, d.scene, F, d.lights, devOut, fetch, d.counters,
+                                 c->countKernels ? d.pathBlocksCount : d.pathBlocks, c->countKernels, st));
+            c->launches++;
+            if (nSlices > 1) {
+                CU_TRY(c, cudaEventRecord(d.evA[sIdx], st));
+                CU_TRY(c, cudaStreamWaitEvent(d.copyStream, d.evA[sIdx], 0));
+                const size_t off = (size_t)(r0 * tileRow), cnt = (size_t)((r1 - r0) * tileRow);
+                CU_TRY(c, cudaMemcpyAsync(hostDst + off, devOut + off, cnt * 4, cudaMemcpyDeviceToHost, d.copyStream));
+            }
+        }
+        if (nSlices > 1 && sliced) *sliced = true;
         if (timeIt) CU_TRY(c, cudaEventRecord(d.ev[1], st));
         CU_TRY(c, cudaEventRecord(d.ev[2], st));
         d.lastStream = st;
@@ -1073,10 +1092,18 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
         }
         XnartFrame f = *frame;
         if (nDev > 1) { f.shardIndex = i; f.shardCount = nDev; f.shardBandRows = 8; }
-        rc = enqueueFrame(c, d, f, d.frameBuf, d.stream);
-        if (rc != XNART_OK) return rc;
-        // device -> host: only the rows this device owns
         uint32_t* hostDst = outPinned ? out : d.pinned;
+        bool sliced = false;
+        // (small scenes: the frame is rendered in a few slices and every slice is copied while the next one renders)
+        rc = enqueueFrame(c, d, f, d.frameBuf, d.stream, false, nullptr, 0, hostDst, &sliced);
+        if (rc != XNART_OK) return rc;
+        if (sliced) {
+            CU_TRY(c, cudaEventRecord(d.evCopied[0], d.copyStream));
+            CU_TRY(c, cudaStreamWaitEvent(d.stream, d.evCopied[0], 0));   // the caller waits on d.stream below
+            CU_TRY(c, cudaEventRecord(d.ev[3], d.stream));
+            continue;
+        }
+        // device -> host: only the rows this device owns
         const int sc = f.shardCount > 1 ? f.shardCount : 1, br = f.shardCount > 1 ? f.shardBandRows : f.vpH;
         for (int b = (sc > 1 ? f.shardIndex : 0); (long long)b * br < f.vpH; b += sc) {
             int y0 = b * br, rows = std::min(br, f.vpH - y0);
