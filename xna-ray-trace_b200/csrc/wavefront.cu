@@ -39,6 +39,9 @@
 #ifndef XN_COOP_LEAF_MAX
 #define XN_COOP_LEAF_MAX 12 // with at most this many lanes holding leaves, the warp tests each leaf cooperatively
 #endif
+#ifndef XN_LEAF_PCT
+#define XN_LEAF_PCT 50      // a round runs the LEAF step when at least this share of the walking lanes hold a leaf, else DESCEND
+#endif
 #ifndef XN_REFILL_MIN
 #define XN_REFILL_MIN 24    // idle lanes that trigger a refill while other lanes are still walking
 #endif
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256, XN_TRACE_MIN_BLOCKS) k_trace(DevScene S, 
         const unsigned nLeaf = (unsigned)__popc(__ballot_sync(FULL, wantLeaf));
         const unsigned nDesc = (unsigned)__popc(__ballot_sync(FULL, walking && !wantLeaf));
         bool over = false;
-        if (nLeaf >= nDesc) {
+        if (nLeaf * 100u >= (nLeaf + nDesc) * (unsigned)XN_LEAF_PCT) {
             if (nLeaf <= XN_COOP_LEAF_MAX) {
                 // few lanes hold leaves: the whole warp serves them one after the other
                 unsigned lm = __ballot_sync(FULL, wantLeaf);
