@@ -797,3 +797,56 @@ def test_measured_peaks_are_plausible(X):
     assert l1 > l2 > hbm > 2e12, (l1, l2, hbm)
     with pytest.raises(X.XnartError):
         X.measure_peak(0, 9)
+
+
+def test_transparent_scene_arena_overflow_is_retried(X, oracle_mod):
+    """Scenes with transparent materials: blocking calls size the path arena for a few nodes per pixel instead of the
+    2^(D+1)-1 worst case, detect an overflow on the device and render again with more room.  scenes.forking_quads_scene
+    forks at nearly every hit (48 rays per pixel at depth 6, far beyond the first guess): the frame, the ray counts, a
+    following flythrough call and a batch of sample casts must still be the oracle's — from a fresh context each, so
+    that every kind of blocking call meets the overflow itself."""
+    import torch
+
+    s = scenes.forking_quads_scene(6)
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    f = s.frame(96, 72)
+    want = o.render_frame(f, n_threads=8)
+    oc = o.counters()
+    assert oc.rays > 40 * 96 * 72 and len(np.unique(want)) > 100
+    near = s.frame(96, 72, camera=scenes.CameraData((0.0, 0.0, 30.0), (0.0, 0.0, 0.0)))
+    want_near = o.render_frame(near, n_threads=8)
+    xy = np.stack(np.meshgrid(np.arange(96), np.arange(72)), -1).reshape(-1, 2).astype(np.float32)
+
+    def fresh():
+        x = X.Xnart()
+        scenes.upload(x, s)
+        return x
+
+    x = fresh()
+    got = x.render_frame(f)
+    assert np.array_equal(want, got), int((want != got).sum())
+    xc = x.counters()
+    for k in ("raysShadow", "raysReflection", "raysRefraction", "hits"):
+        assert getattr(oc, k) == getattr(xc, k), k
+    assert np.array_equal(x.render_frame(f), want)        # the scale sticks: no second retry, same frame
+    x.close()
+    x = fresh()
+    two = x.render_frames([near, f])
+    assert np.array_equal(two[0], want_near) and np.array_equal(two[1], want)
+    x.close()
+    x = fresh()
+    assert np.array_equal(x.cast_rays(f, xy).reshape(72, 96), want)
+    x.close()
+    x = fresh()
+    dev = torch.zeros((72, 96), dtype=torch.int32, device="cuda:0")
+    x.render_frame_device(f, dev.data_ptr())
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), want)
+    # on a caller's stream nothing can be retried: the arena keeps its worst-case size and the frame is right at once
+    st = torch.cuda.Stream()
+    dev.zero_()
+    torch.cuda.synchronize()
+    x.render_frame_device(f, dev.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), want)
+    x.close()

@@ -112,6 +112,15 @@ struct XnartCtx {
     int nPairs = 0;          // > 0: the scene octree is a single leaf (wavefront path available)
     SmallScene small{};      // the whole intersection data set as a kernel parameter (path.cu), when it fits
     bool smallOk = false;
+    // Transparent materials can fork every hit into reflection + refraction (RayTracer.cs:586-702): the worst case is a full
+    // binary tree per pixel, 2^(D+1)-1 path nodes — 511 at the reference's depth of 8, which cut a 1080p frame of the default
+    // 4-sphere scene into 11 arena chunks of ~18 launches each although only 3 % of its pixels hit anything.  Blocking render
+    // calls therefore size the arena for arenaScale x (D+1) nodes per pixel, detect an overflow on the device, and render the
+    // frame again with four times the room (the scale sticks to the context); calls on a caller's stream cannot look at the
+    // flag before they return and keep the worst-case size.
+    double arenaScale = 2.0;
+    bool optimisticArena = false;   // set by the blocking entry points around their enqueue
+    bool overflowed = false;        // collectCounters saw the overflow flag
     bool keepCounters = false;  // XNART_OPT_KEEP_COUNTERS: statistics accumulate over render calls
     bool pathKernel = true;  // XNART_OPT_PATH_KERNEL: small opaque scenes render a frame with one persistent launch
     std::vector<float> hostInner;            // expansion records as uploaded (32 floats per internal node)
@@ -715,9 +724,12 @@ static bool useWave(const XnartCtx* c, const DeviceState& d) {
     if (c->nPairs <= 0 || d.traceBlocks <= 0 || d.traceBlocksCount <= 0) return false;
     if (c->traversalMode == 1) return false;
     if (c->traversalMode == 2) return true;
-    // small meshes (e.g. the 960-triangle spheres of the reference's default scene) do not have the
-    // heavy-tailed queries the persistent kernel is for, and its fixed launch sequence costs more there
-    return deepScene(c) && c->totalRefs >= 65536;
+    // Any octree of depth >= 2.  Even the 960-triangle spheres of the reference's default scene (Game1.cs:98-107) belong
+    // here: their deep recursion levels hold a few thousand rays that start ON a sphere and cross its whole octree, one
+    // thread per ray leaves a handful of warps walking them serially (ncu launch list: levels 1-5 take 300-490 us each for
+    // 12 K hits), while the persistent kernel serves those leaves with whole warps and splits the queries — 512x512:
+    // 1.93 -> 0.81 ms, 1920x1080: 2.48 -> 1.18 ms.
+    return deepScene(c);
 }
 
 // One persistent launch per frame (path.cu) for small opaque scenes.
@@ -814,8 +826,12 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     d.lastPath = false;
     // worst-case arena per pixel: a chain of D+1 path nodes, or a full binary tree when a
     // transparent material can fork every hit into reflection + refraction (RayTracer.cs:586-702)
-    const double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
-    const double raysPerPixel = c->hasTransparent ? std::ldexp(1.0, D) : 1.0;
+    double nodesPerPixel = c->hasTransparent ? (std::ldexp(1.0, D + 1) - 1.0) : (double)(D + 1);
+    double raysPerPixel = c->hasTransparent ? std::ldexp(1.0, D) : 1.0;
+    if (c->hasTransparent && c->optimisticArena) {   // see XnartCtx::arenaScale
+        nodesPerPixel = std::min(nodesPerPixel, c->arenaScale * (double)(D + 1));
+        raysPerPixel = std::min(raysPerPixel, c->arenaScale);
+    }
     const bool wave = !mono && useWave(c, d);
     const double bytesPerPixel = nodesPerPixel * 48.0 + raysPerPixel * (80.0 + (wave ? 2.0 * (32.0 + 72.0 * std::max(F.nLights, 1)) : 0.0)) + 64.0;
     long long chunk = (long long)std::floor((double)c->arenaLimit / bytesPerPixel);
@@ -925,6 +941,14 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     return XNART_OK;
 }
 
+// After an arena overflow in a blocking call: four times the room, unless the worst case was already provided.
+static bool growArena(XnartCtx* c) {
+    if (!c->overflowed || !c->hasTransparent || c->arenaScale >= 1.0e9) return false;
+    c->overflowed = false;
+    c->arenaScale *= 4.0;
+    return true;
+}
+
 // Brackets of a blocking render call for xnart_progress.
 static void beginProgress(XnartCtx* c, unsigned long long totalPixels) {
     for (DeviceState& d : c->devs) {
@@ -957,7 +981,11 @@ static int collectCounters(XnartCtx* c) {
         unsigned ovf = 0;
         CU_TRY(c, cudaMemcpy(h, d.counters, sizeof h, cudaMemcpyDeviceToHost));
         CU_TRY(c, cudaMemcpy(&ovf, d.levelWords + 2 * (kMaxLevels + 2), sizeof ovf, cudaMemcpyDeviceToHost));
-        if (ovf) return fail(c, XNART_ERR_OUT_OF_MEMORY, "internal: ray queue overflow");
+        if (ovf) {
+            c->overflowed = true;
+            d.countersPending = false;
+            return fail(c, XNART_ERR_OUT_OF_MEMORY, "ray queue overflow: the path arena was too small for this frame");
+        }
         t.pixels += (uint64_t)d.lastPixels;
         t.raysPrimary += (uint64_t)d.lastPixels;
         t.hits += h[CTR_HITS];
@@ -986,10 +1014,8 @@ static int collectCounters(XnartCtx* c) {
     return XNART_OK;
 }
 
-int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* devOut, void* cudaStream) {
+static int renderFrameDeviceBody(XnartCtx* c, const XnartFrame* frame, void* devOut, void* cudaStream) {
     if (!c || !devOut) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frame_device: bad arguments");
-    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
-    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");  // RayTracer.cs:62-63
     if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
     if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
     int rc = validateFrame(c, frame);
@@ -1044,10 +1070,8 @@ int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* de
     return rc;
 }
 
-int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) {
+static int renderFrameBody(XnartCtx* c, const XnartFrame* frame, uint32_t* out) {
     if (!c || !out) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frame: bad arguments");
-    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
-    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
     if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
     if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
     int rc = validateFrame(c, frame);
@@ -1143,10 +1167,8 @@ int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) 
 // after frame): n frames of one viewport size into n consecutive host frames.  Frame f is rendered by
 // device f % nDevices; on each device the device->host copy of a frame overlaps the rendering of
 // the next one (two frame buffers, a copy stream).  Replaces n x RenderInternal + SetData.
-int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, uint32_t* out) {
+static int renderFramesBody(XnartCtx* c, const XnartFrame* frames, int32_t n, uint32_t* out) {
     if (!c || n < 0 || (n > 0 && (!frames || !out))) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames: bad arguments");
-    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
-    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
     if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
     if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
     if (n == 0) return XNART_OK;
@@ -1249,10 +1271,8 @@ int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, ui
 // times in xnart_create keeps k frames in flight).  The work is ordered after what is already enqueued on
 // `cudaStream` and the stream is made to wait for all of it, so the caller can chain a collective or a copy;
 // with a NULL stream the call returns after completion.
-int32_t xnart_render_frames_device(XnartCtx* c, const XnartFrame* frames, int32_t n, void* devOut, void* cudaStream) {
+static int renderFramesDeviceBody(XnartCtx* c, const XnartFrame* frames, int32_t n, void* devOut, void* cudaStream) {
     if (!c || n < 0 || (n > 0 && (!frames || !devOut))) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_render_frames_device: bad arguments");
-    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
-    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
     if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
     if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
     if (n == 0) return XNART_OK;
@@ -1326,10 +1346,8 @@ static cudaError_t ensureScratch(DeviceState& d, size_t bytes) {
 // (RayTracer.cs:220-276) — Unproject (x, y, 0) and (x, y, 1), normalise, CastRay at iteration 0.
 // screenXY = n x (x, y) in viewport pixel units (sub-pixel positions allowed), rgba8Out = n colours.
 // The adaptive refinement around it (RayTracer.cs:279-309) is host logic (host.py).
-int32_t xnart_cast_rays(XnartCtx* c, const XnartFrame* frame, const float* screenXY, int64_t n, uint32_t* out) {
+static int castRaysBody(XnartCtx* c, const XnartFrame* frame, const float* screenXY, int64_t n, uint32_t* out) {
     if (!c || n < 0 || (n > 0 && (!screenXY || !out))) return fail(c, XNART_ERR_INVALID_ARGUMENT, "xnart_cast_rays: bad arguments");
-    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);
-    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");
     if (c->devs.empty()) return fail(c, XNART_ERR_NO_DEVICE, "host-only context: libxnart has no CPU fallback");
     if (!c->built) return fail(c, XNART_ERR_NOT_BUILT, "xnart_build_scene has not been called");
     int rc = validateFrame(c, frame);
@@ -1359,6 +1377,38 @@ int32_t xnart_cast_rays(XnartCtx* c, const XnartFrame* frame, const float* scree
     c->last.msTotal = c->last.msLevels + c->last.msResolve;
     return rc;
 }
+
+// ---- public render entry points: one render in flight per context (RayTracer.cs:62-63), and — for calls that return
+// after completion — the arena-overflow retry described at XnartCtx::arenaScale.
+#define XNART_RENDER_ENTRY(blocking, call)                                                                          \
+    if (!c) return fail(nullptr, XNART_ERR_INVALID_ARGUMENT, "null context");                                       \
+    std::unique_lock<std::mutex> lk(c->renderMutex, std::try_to_lock);                                              \
+    if (!lk.owns_lock()) return fail(nullptr, XNART_ERR_BUSY, "a render is already in flight");                     \
+    int rc;                                                                                                         \
+    do {                                                                                                            \
+        c->optimisticArena = (blocking);                                                                            \
+        c->overflowed = false;                                                                                      \
+        rc = (call);                                                                                                \
+        c->optimisticArena = false;                                                                                 \
+    } while ((blocking) && rc == XNART_ERR_OUT_OF_MEMORY && growArena(c));                                          \
+    return rc;
+
+int32_t xnart_render_frame_device(XnartCtx* c, const XnartFrame* frame, void* devOut, void* cudaStream) {
+    XNART_RENDER_ENTRY(cudaStream == nullptr, renderFrameDeviceBody(c, frame, devOut, cudaStream))
+}
+int32_t xnart_render_frame(XnartCtx* c, const XnartFrame* frame, uint32_t* out) {
+    XNART_RENDER_ENTRY(true, renderFrameBody(c, frame, out))
+}
+int32_t xnart_render_frames(XnartCtx* c, const XnartFrame* frames, int32_t n, uint32_t* out) {
+    XNART_RENDER_ENTRY(true, renderFramesBody(c, frames, n, out))
+}
+int32_t xnart_render_frames_device(XnartCtx* c, const XnartFrame* frames, int32_t n, void* devOut, void* cudaStream) {
+    XNART_RENDER_ENTRY(cudaStream == nullptr, renderFramesDeviceBody(c, frames, n, devOut, cudaStream))
+}
+int32_t xnart_cast_rays(XnartCtx* c, const XnartFrame* frame, const float* screenXY, int64_t n, uint32_t* out) {
+    XNART_RENDER_ENTRY(true, castRaysBody(c, frame, screenXY, n, out))
+}
+#undef XNART_RENDER_ENTRY
 
 int32_t xnart_trace_rays(XnartCtx* c, const float* rays6, int64_t n, const int32_t* ignore2, int32_t* objId, int32_t* meshId,
                          int32_t* triId, float* u, float* v, float* dOut, float* worldPos3) {

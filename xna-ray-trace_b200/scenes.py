@@ -382,6 +382,27 @@ def soup_scene(n=10_000_000, max_reflections=8, half=100.0):
     return s.finalize()
 
 
+def forking_quads_scene(depth=6):
+    """Five parallel transparent quads, three facing the camera and two facing away (invisible to primary rays: back
+    faces), refraction index 1: every hit forks into a reflection that turns round and a refraction that goes straight
+    on, both towards more quads — the binary path tree of RayTracer.cs:586-702 at nearly full width (48 rays per pixel
+    at depth 6).  A stress case for the path arena of transparent scenes."""
+    def quad(z, flip):
+        a, b, c = [(-5, -5, z), (5, 5, z)], [(-5, 5, z), (5, -5, z)], [(5, -5, z), (-5, 5, z)]
+        if flip:
+            b, c = c, b
+        return make_triangles(a, b, c, color=(0.6, 0.8, 1.0, 0.5))
+
+    s = SceneData("forking_quads")
+    for z, flip in ((0.0, False), (-2.0, False), (-4.0, False), (2.0, True), (4.0, True)):
+        s.meshes.append(MeshData(quad(z, flip), reflectiveness=0.5, transparent=True, refraction_index=1.0))
+        s.objects.append(ObjectData([len(s.meshes) - 1]))
+    s.lights.append(spot_light((0.0, 3.0, 12.0)))
+    s.camera = CameraData((0.3, 0.2, 10.0), (0.0, 0.0, 0.0))
+    s.max_reflections = depth
+    return s.finalize()
+
+
 def spheres_scene():
     """The shipped default scene (Game1.cs:98-138): 4 instances of one transparent sphere."""
     s = SceneData("default_spheres")
