@@ -1,7 +1,7 @@
 // path.cu — the trace loop for SMALL opaque scenes (the Free_crate configs of BASELINE.json) as ONE
 // persistent kernel per frame (hand-written CUDA, sm_100a).
 //
-// Eligible scenes (xnart_capi.cu: buildSmallScene): the OctreeSpatialManager tree is a single leaf
+// Eligible scenes (xnart_capi.cu: xnart_build_scene): the OctreeSpatialManager tree is a single leaf
 // (<= itemTreshold objects, OctreeSpatialManager.cs:103), every MeshOctree is a single leaf
 // (<= itemTreshold triangles, MeshOctree.cs:86), no material is transparent, and the pairs / leaf
 // references fit SmallScene.  Everything else keeps the level kernels (kernels.cu) or the wavefront
