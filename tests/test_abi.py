@@ -187,3 +187,30 @@ def test_expansion_records_describe_the_trees(xnart_lib, name):
             checked += 1
     assert checked > (0 if name == "spheres" else 50) or name == "spheres"
     x.close()
+
+
+def test_reference_arm_prints_the_bench_contract():
+    """`bench.py --impl reference` (the oracle on the host cores) prints ONE JSON line with the contract's keys and the
+    same `config` dictionary as the own arm (bench.bench_config), so that the driver compares like with like."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+    from xna_ray_trace_b200 import scenes
+
+    assert d["config"] == bench.bench_config(scenes.crate_scene(), 128)
+    assert d["config"]["workload"] == "free_crate_1080p_depth8"

@@ -32,18 +32,28 @@ def gather_bands(part, height, world, band_rows_, rank, dst=0):
     if height % band_rows_ == 0:
         nb = height // band_rows_
         v = part.view(nb, band_rows_, *part.shape[1:])
-        mine = v[rank::world].contiguous()
         counts = [len(range(r, nb, world)) for r in range(world)]
-        even = len(set(counts)) == 1
+        cmax = max(counts)
+        mine = v[rank::world]
+        if counts[rank] < cmax:
+            # ranks with one band fewer pad their share, so that ONE equal-size collective serves uneven splits too
+            # (2160 rows in 8-row bands over 8 ranks: 34 or 33 bands each) instead of a send / receive per rank
+            pad = torch.zeros((cmax - counts[rank],) + tuple(v.shape[1:]), dtype=part.dtype, device=part.device)
+            mine = torch.cat([mine, pad])
+        else:
+            mine = mine.contiguous()
         if rank == dst:
-            bufs = [torch.empty((counts[r],) + tuple(v.shape[1:]), dtype=part.dtype, device=part.device) for r in range(world)]
-            dist.gather(mine, bufs, dst=dst) if even else _gather_uneven(mine, bufs, rank, world, dst)
+            recv = torch.empty((world, cmax) + tuple(v.shape[1:]), dtype=part.dtype, device=part.device)
+            dist.gather(mine, list(recv.unbind(0)), dst=dst)
             full = torch.empty_like(part)
             fv = full.view(nb, band_rows_, *part.shape[1:])
-            for r in range(world):
-                fv[r::world] = bufs[r]
+            whole = (nb // world) * world          # bands every rank owns the same number of: one strided copy
+            if whole:
+                fv[:whole].view(nb // world, world, *v.shape[1:]).copy_(recv[:, : nb // world].transpose(0, 1))
+            for r in range(nb - whole):            # the last, incomplete round
+                fv[whole + r] = recv[r, nb // world]
             return full
-        dist.gather(mine, None, dst=dst) if even else _gather_uneven(mine, None, rank, world, dst)
+        dist.gather(mine, None, dst=dst)
         return None
     rows = torch.tensor(band_rows(height, rank, world, band_rows_), device=part.device, dtype=torch.long)
     mine = part.index_select(0, rows).contiguous()
