@@ -686,7 +686,9 @@ def flythrough_avi(x, scene, n_frames, world, rank, dev, torch, dist):
         except Exception as e:
             err, sink = "cannot create the AVI file: %s" % e, None
     # warm-up round outside the timed region (arena allocation, NCCL channels)
-    flythrough.render_flythrough(x, scene, cams[:2 * world], W, H, sink=None, world=world, rank=rank, batch=2, dib24=True)
+    # (rank 0 gets a sink that discards: the page-locked staging buffers of the real run are allocated here)
+    flythrough.render_flythrough(x, scene, cams[:8 * world], W, H, sink=flythrough.NullSink(W, H) if rank == 0 else None,
+                                 world=world, rank=rank, batch=8, dib24=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
