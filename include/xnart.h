@@ -115,8 +115,9 @@ typedef struct XnartCounters {
 
 enum {
     XNART_OPT_COUNTERS = 1,      /* 0/1: run the instrumented kernels (slower) */
-    XNART_OPT_ARENA_BYTES = 2,   /* upper bound for the per-render path arena (default 8 GiB) */
-    XNART_OPT_SEMANTICS = 3,     /* default semantics for xnart_trace_rays */
+    XNART_OPT_ARENA_BYTES = 2,   /* upper bound for the per-render path arena (default 8 GiB); larger frames are rendered in chunks.
+                                    Scenes with transparent materials start from a small arena and grow it on overflow (blocking calls) */
+    XNART_OPT_SEMANTICS = 3,     /* framework arithmetic of xnart_trace_rays: XNART_SEMANTICS_XNA40 (default) or _MONOGAME */
     XNART_OPT_TRAVERSAL = 4,     /* kernel schedule: 0 auto, 1 one thread per ray, 2 wavefront (persistent trace kernel) */
     XNART_OPT_FUSE_FRAME = 5,    /* 0/1 (default 0): shallow scenes render a frame in one cooperative launch */
     XNART_OPT_OVERLAP_LEVELS = 6, /* 0/1 (default 1): wavefront path runs a level's shadow batch beside the next level */
@@ -139,7 +140,8 @@ typedef struct XnartCtx XnartCtx;
  * A device id may be listed several times: every entry is an independent in-flight state (stream,
  * path arena, scene copy) and xnart_render_frames deals whole frames round-robin over the entries,
  * so k entries for one GPU keep k frames in flight on it (their launch sequences fill each other's
- * gaps: 13.5 vs 10.7 Grays/s on the 1080p crate flythrough with k = 3).  xnart_render_frame splits a
+ * gaps and tails: 26.9 vs 22.0 Grays/s on the 1080p crate flythrough with k = 2).  On deep scenes xnart_render_frame_device
+ * also renders ONE frame as k sub-shards side by side.  xnart_render_frame splits a
  * single frame over distinct GPUs only. */
 int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds);
 int32_t xnart_destroy(XnartCtx* ctx);
