@@ -8,7 +8,8 @@ from xna_ray_trace_b200 import capi, records, scenes
 
 name, W, H = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 n = int(sys.argv[4]) if len(sys.argv) > 4 else 4
-s = {"crate": scenes.crate_scene, "grid": lambda: scenes.grid_scene(707), "spheres": scenes.spheres_scene}[name]()
+s = {"crate": scenes.crate_scene, "grid": lambda: scenes.grid_scene(707), "spheres": scenes.spheres_scene,
+     "soup": lambda: scenes.soup_scene(10_000_000)}[name]()
 x = capi.Xnart(devices=(0,))
 for kv in sys.argv[5:]:
     k, v = kv.split("=")
