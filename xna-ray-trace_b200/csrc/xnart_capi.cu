@@ -203,8 +203,9 @@ int32_t xnart_create(XnartCtx** out, int32_t nDevices, const int32_t* deviceIds)
                 cudaEventCreateWithFlags(&d.evRendered[k], cudaEventDisableTiming);
                 cudaEventCreateWithFlags(&d.evCopied[k], cudaEventDisableTiming);
             }
-            cudaMalloc(&d.levelWords, sizeof(unsigned) * kLevelWords);
-            cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounterSlots);
+            // counters and level words share one block so one copy reads the counters and the overflow flag
+            cudaMalloc(&d.counters, sizeof(unsigned long long) * kCounterSlots + sizeof(unsigned) * kLevelWords);
+            d.levelWords = reinterpret_cast<unsigned*>(d.counters + kCounterSlots);
             cudaMalloc(&d.stamps, sizeof(unsigned long long) * 4);
             int coopOk = 0;
             cudaDeviceGetAttribute(&coopOk, cudaDevAttrCooperativeLaunch, id);
@@ -227,7 +228,7 @@ int32_t xnart_destroy(XnartCtx* c) {
         cudaSetDevice(d.dev);
         cudaStreamSynchronize(d.stream);
         freeScene(d);
-        cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.levelWords); cudaFree(d.counters); cudaFree(d.stamps); cudaFree(d.frameBuf);
+        cudaFree(d.lights); cudaFree(d.arenaBlock); cudaFree(d.counters); cudaFree(d.stamps); cudaFree(d.frameBuf);
         if (d.pinned) cudaFreeHost(d.pinned);
         if (d.progressHost) cudaFreeHost(d.progressHost);
         cudaFree(d.scratch);
@@ -977,10 +978,11 @@ static int collectCounters(XnartCtx* c) {
         any = true;
         CU_TRY(c, cudaSetDevice(d.dev));
         if (d.lastStream) CU_TRY(c, cudaStreamSynchronize(d.lastStream));
-        unsigned long long h[kCounterSlots];
-        unsigned ovf = 0;
-        CU_TRY(c, cudaMemcpy(h, d.counters, sizeof h, cudaMemcpyDeviceToHost));
-        CU_TRY(c, cudaMemcpy(&ovf, d.levelWords + 2 * (kMaxLevels + 2), sizeof ovf, cudaMemcpyDeviceToHost));
+        constexpr int kOvfWord = 2 * (kMaxLevels + 2);
+        struct { unsigned long long h[kCounterSlots]; unsigned words[kOvfWord + 1]; } got;
+        CU_TRY(c, cudaMemcpy(&got, d.counters, sizeof got, cudaMemcpyDeviceToHost));
+        const unsigned long long* h = got.h;
+        const unsigned ovf = got.words[kOvfWord];
         if (ovf) {
             c->overflowed = true;
             d.countersPending = false;
