@@ -138,6 +138,7 @@ struct DevFrame {
     float inv[16];       // Invert(Identity * view * proj), computed once per frame on the host
     int vpX, vpY, vpW, vpH;
     float minDepth, maxDepth;
+    float ndcZ[2];          // (0 - minDepth) / (maxDepth - minDepth) and (1 - minDepth) / (maxDepth - minDepth), IEEE fp32 on the host
     int maxReflections, filtering, addressMode, semantics;
     int shardIndex, shardCount, shardBandRows;
     int nLights;

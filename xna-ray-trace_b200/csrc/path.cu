@@ -39,6 +39,9 @@
 #ifndef XN_PATH_UNROLL
 #define XN_PATH_UNROLL 2       // triangles of the back-face pass in flight per lane
 #endif
+#ifndef XN_PATH_EARLY
+#define XN_PATH_EARLY 1         // leave the full triangle test after u when u is out of range
+#endif
 #ifndef XN_PATH_REFILL_MIN
 #define XN_PATH_REFILL_MIN 24   // idle lanes that trigger a refill while other lanes are still on a path
 #endif
@@ -139,10 +142,17 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
                     const V3 E1 = mk(b.x, b.y, b.z), E2 = mk(c.x, c.y, c.z), V1 = mk(a.x, a.y, a.z);
                     const V3 T = sub(r.o, V1);
                     const V3 Pv = cross(r.d, E2);
-                    const V3 Q = cross(T, E1);
-                    const float row1 = dot(Q, E2), row2 = dot(Pv, T), row3 = dot(Q, r.d);
+                    const float row2 = dot(Pv, T);
                     const float inv = 1.0f / dot(Pv, E1);
-                    const float dist = inv * row1, uu = inv * row2, vv = inv * row3;
+                    const float uu = inv * row2;
+#if XN_PATH_EARLY
+                    // u alone rejects most candidates: 0 <= u, and u <= u + v <= 1 for every accepted v >= 0 (rounding
+                    // is monotone), so a lane outside [0, 1] cannot pass the test below whatever v and dist are
+                    if (!(uu >= 0.0f && uu <= 1.0f)) continue;
+#endif
+                    const V3 Q = cross(T, E1);
+                    const float row1 = dot(Q, E2), row3 = dot(Q, r.d);
+                    const float dist = inv * row1, vv = inv * row3;
                     if (uu >= 0.0f && vv >= 0.0f && dist >= 0.0f && (uu + vv) <= 1.0f && dist < bd) {
                         bd = dist;
                         out.u = uu; out.v = vv; out.tri = __float_as_int(nt.w); out.key = P.refBase + c0 + i;
@@ -194,8 +204,8 @@ __device__ __forceinline__ void primaryRay(const DevFrame& F, unsigned idx, V3& 
         pixelOf32(F, (unsigned)F.pixelBase + idx, x, y);
         sx = (float)x; sy = (float)y;
     }
-    o = unproject(F, sx, sy, 0.0f);
-    const V3 farP = unproject(F, sx, sy, 1.0f);
+    o = unproject(F, sx, sy, F.ndcZ[0]);
+    const V3 farP = unproject(F, sx, sy, F.ndcZ[1]);
     d = normalize(sub(farP, o));
 }
 

@@ -39,12 +39,15 @@ __device__ __forceinline__ void pixelOf(const DevFrame& F, long long q, int& x, 
     }
 }
 
-// Viewport.Unproject with the frame-constant inverse.
-__device__ __forceinline__ V3 unproject(const DevFrame& F, float sx, float sy, float sz) {
+// Viewport.Unproject with the frame-constant inverse.  `ndcZ` is the source depth after
+// (z - MinDepth) / (MaxDepth - MinDepth): the two depths Render uses (0 and 1, RayTracer.cs:414-415) are divided once
+// per frame on the host (DevFrame.ndcZ) — with MinDepth = 0 the near one is 0 / 1, and a zero dividend sends the
+// device's IEEE division through its slow-path subroutine for every pixel.
+__device__ __forceinline__ V3 unproject(const DevFrame& F, float sx, float sy, float ndcZ) {
     V3 s;
     s.x = (((sx - (float)F.vpX) / (float)F.vpW) * 2.0f) - 1.0f;
     s.y = -((((sy - (float)F.vpY) / (float)F.vpH) * 2.0f) - 1.0f);
-    s.z = (sz - F.minDepth) / (F.maxDepth - F.minDepth);
+    s.z = ndcZ;
     const float* m = F.inv;
     V3 v = mk((((s.x * m[0]) + (s.y * m[4])) + (s.z * m[8])) + m[12],
               (((s.x * m[1]) + (s.y * m[5])) + (s.z * m[9])) + m[13],
@@ -75,8 +78,8 @@ __device__ __forceinline__ RayIn loadRay(const DevFrame& F, const DevArena& A, i
             pixelOf(F, F.pixelBase + idx, x, y);
             sx = (float)x; sy = (float)y;
         }
-        r.o = unproject(F, sx, sy, 0.0f);
-        V3 farP = unproject(F, sx, sy, 1.0f);
+        r.o = unproject(F, sx, sy, F.ndcZ[0]);
+        V3 farP = unproject(F, sx, sy, F.ndcZ[1]);
         r.d = normalize(sub(farP, r.o));
         r.ignM = -1; r.ignT = -1; r.refIndex = 1.0f;
     } else {

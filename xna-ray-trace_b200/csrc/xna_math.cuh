@@ -121,9 +121,19 @@ XD uint32_t packColor(V3 c, int semantics) {
     else { r = packChannelXna40(c.x); g = packChannelXna40(c.y); b = packChannelXna40(c.z); }
     return r | (g << 8) | (b << 16) | 0xFF000000u;
 }
+// byte / 255f.  On the device a zero dividend takes the IEEE division's slow-path subroutine (ncu: 177 k warp-level calls
+// per crate frame, black being the colour of every miss), so 0 is divided as 1 and selected back to 0.0f = 0 / 255.
+XD float byteToUnit(uint32_t b) {
+#ifdef __CUDA_ARCH__
+    const float q = (float)(b | (uint32_t)(b == 0u)) / 255.0f;
+    return b ? q : 0.0f;
+#else
+    return (float)b / 255.0f;
+#endif
+}
 // Color.ToVector3(): byte / 255f
 XD V3 unpackColor(uint32_t c) {
-    return mk((float)(c & 255u) / 255.0f, (float)((c >> 8) & 255u) / 255.0f, (float)((c >> 16) & 255u) / 255.0f);
+    return mk(byteToUnit(c & 255u), byteToUnit((c >> 8) & 255u), byteToUnit((c >> 16) & 255u));
 }
 
 }  // namespace xn

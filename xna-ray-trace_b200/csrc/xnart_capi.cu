@@ -773,6 +773,12 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     }
     F.vpX = f.vpX; F.vpY = f.vpY; F.vpW = f.vpW; F.vpH = f.vpH;
     F.minDepth = f.minDepth; F.maxDepth = f.maxDepth;
+    {   // Viewport.Unproject's source.Z for the near and far points (shade.cuh: unproject); volatile keeps the two IEEE
+        // fp32 operations as written whatever the host compiler would like to fold
+        volatile float lo = f.minDepth, range = f.maxDepth - f.minDepth;
+        F.ndcZ[0] = (0.0f - lo) / range;
+        F.ndcZ[1] = (1.0f - lo) / range;
+    }
     F.maxReflections = f.maxReflections; F.filtering = f.filtering; F.addressMode = f.addressMode; F.semantics = f.semantics;
     F.shardIndex = f.shardCount > 1 ? f.shardIndex : 0;
     F.shardCount = f.shardCount > 1 ? f.shardCount : 1;
