@@ -209,12 +209,12 @@ struct SmallPair {
     int first, count;    // run of the mesh's leaf in SmallScene.tri (4 float4 per reference)
     int refBase;         // global position of the run's first reference in refs[] / leafTri
     int boxCoversRoot;   // 1: rootBox lies inside box component-wise (the Mesh.RayIntersects prefilter cannot reject alone)
-    int _pad;
+    int identity;        // 1: reference k of the run is triangle k of the mesh (the ignored triangle is found by position)
 };
 static_assert(sizeof(SmallPair) == 176, "SmallPair layout");
 struct SmallScene {
     SmallPair pair[kSmallPairs];
-    float4 tri[4 * kSmallTris];   // same 64-byte records as leafTri
+    float4 tri[4 * (kSmallTris + 3)];   // same 64-byte records as leafTri; 3 zero records so that runs can be read in fours
     float sceneBox[6];            // bounds of the scene octree root
     int nPairs;
     int _pad;

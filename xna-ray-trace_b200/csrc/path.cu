@@ -31,7 +31,7 @@
 #define XN_PATH_THREADS 128
 #endif
 #ifndef XN_PATH_MIN_BLOCKS
-#define XN_PATH_MIN_BLOCKS 6
+#define XN_PATH_MIN_BLOCKS 7
 #endif
 #ifndef XN_PATH_BATCH
 #define XN_PATH_BATCH 32        // pixels a warp takes from the frame per atomic (one 8x4 tile)
@@ -57,8 +57,21 @@ __device__ __forceinline__ V3 transform43p(V3 p, const float* m) {
               (((p.x * m[1]) + (p.y * m[4])) + (p.z * m[7])) + m[10],
               (((p.x * m[2]) + (p.y * m[5])) + (p.z * m[8])) + m[11]);
 }
-__device__ __forceinline__ bool slab6(const float* b, const RayPre& r, float& t) {
-    return slab(make_float3(b[0], b[1], b[2]), make_float3(b[3], b[4], b[5]), r, t);
+// BoundingBox.Intersects(ref Ray) against a box of the SmallScene.  `anyPar` (warp-uniform): some lane's ray has a
+// component below the framework's 1e-6 threshold; otherwise every lane takes the three non-parallel axes of slabAxis
+// (trace.cuh) — the same operations in the same order, without the predicated parallel-axis code, which made up half
+// of the slab test's instructions (ncu, profiles/r02k: 55 warp instructions per box, 3.7 boxes per query).
+__device__ __forceinline__ bool slab6(const float* b, const RayPre& r, bool anyPar, float& t) {
+    if (anyPar) return slab(make_float3(b[0], b[1], b[2]), make_float3(b[3], b[4], b[5]), r, t);
+    float tmin = 0.0f, tmax = FLT_MAX;
+    const float x1 = (b[0] - r.o.x) * r.inv.x, x2 = (b[3] - r.o.x) * r.inv.x;
+    tmin = fmaxf(fminf(x1, x2), tmin); tmax = fminf(fmaxf(x1, x2), tmax);
+    const float y1 = (b[1] - r.o.y) * r.inv.y, y2 = (b[4] - r.o.y) * r.inv.y;
+    tmin = fmaxf(fminf(y1, y2), tmin); tmax = fminf(fmaxf(y1, y2), tmax);
+    const float z1 = (b[2] - r.o.z) * r.inv.z, z2 = (b[5] - r.o.z) * r.inv.z;
+    tmin = fmaxf(fminf(z1, z2), tmin); tmax = fminf(fmaxf(z1, z2), tmax);
+    t = tmin;
+    return !(tmin > tmax);
 }
 
 // OctreeSpatialManager.GetRayIntersection (OctreeSpatialManager.cs:312-455) for a SmallScene, called by
@@ -77,10 +90,19 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
     const unsigned FULL = 0xffffffffu;
     bool live = act && finite3(ro) && finite3(rd);
     {
-        const RayPre rw = prepRay(ro, rd);
-        float t0;
+        // The scene root's slab test (:457-461).  A finite ray that starts inside the box (bounds included) passes it
+        // whatever its direction: on a non-parallel axis (mn - p) <= 0 <= (mx - p) exactly, the reciprocal is finite and
+        // non-zero, so one product is <= 0 and the other >= 0, tmin stays 0 and tmax >= 0; a parallel axis tests p in
+        // [mn, mx].  Shadow and reflection rays start on a surface, i.e. inside: when no lane of the warp starts outside,
+        // the world-space reciprocals and the test are skipped (the verdict is known), else all lanes run it.
+        const float* sb = SS.sceneBox;
+        const bool inside = ro.x >= sb[0] && ro.x <= sb[3] && ro.y >= sb[1] && ro.y <= sb[4] && ro.z >= sb[2] && ro.z <= sb[5];
         if (COUNT && live) ctr.nBox++;
-        live = slab6(SS.sceneBox, rw, t0) && live;
+        if (__any_sync(FULL, live && !inside)) {
+            const RayPre rw = prepRay(ro, rd);
+            float t0;
+            live = slab6(SS.sceneBox, rw, __any_sync(FULL, rw.par != 0), t0) && live;
+        }
     }
     float bd = FLT_MAX;
     out.obj = out.mesh = out.tri = -1; out.key = 0; out.u = out.v = 0.0f; out.d = 0.0f;
@@ -89,7 +111,7 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
     int cls = -1;
     RayPre r;
     r.o = r.d = r.inv = mk(0.0f, 0.0f, 0.0f); r.par = r.oct = 0;
-    bool rOk = false;
+    bool rOk = false, rPar = false;
 #pragma unroll 1
     for (int p = 0; p < SS.nPairs; p++) {
         const SmallPair& P = SS.pair[p];
@@ -101,6 +123,7 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
             const V3 dd = normalize(sub(v2, v1));
             rOk = finite3(v1) && finite3(dd);   // a non-finite ray fails every triangle test (NaN comparisons)
             r = prepRay(v1, dd);
+            rPar = __any_sync(FULL, r.par != 0);
         }
         bool go = live && rOk;
         float tb, ct;
@@ -110,10 +133,10 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
         // bounds — so the verdict of the pair is the root test's alone; the instrumented build still runs it.
         if (COUNT || !P.boxCoversRoot) {
             if (COUNT && go) ctr.nBox++;
-            go = slab6(P.box, r, tb) && go;
+            go = slab6(P.box, r, rPar, tb) && go;
         }
         if (COUNT && go) ctr.nBox++;
-        go = slab6(P.rootBox, r, ct) && go;     // root of the MeshOctree (MeshOctree.cs:331)
+        go = slab6(P.rootBox, r, rPar, ct) && go;     // root of the MeshOctree (MeshOctree.cs:331)
         if (!__any_sync(FULL, go)) continue;
         const int ign = (ignM == P.mesh) ? ignT : -1;
         V3 po = mk(0.0f, 0.0f, 0.0f);
@@ -124,13 +147,33 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
             const float4* __restrict__ T4 = SS.tri + 4 * (P.first + c0);
             // pass 1: reference identity (:290) and back-face test (RayExtensions.cs:46-51) -> bit mask
             unsigned m = 0u;
+            if (!COUNT && P.identity) {
+                // the k-th reference of the run is triangle k (a single-leaf MeshOctree built from the mesh's own list):
+                // the ignored triangle is bit `ign - c0`, cleared once after the loop; groups of four with constant bit
+                // positions (SmallScene.tri is padded, the bits past n are cleared below)
+#pragma unroll 1
+                for (int i0 = 0; i0 < n; i0 += 4) {
+                    unsigned nib = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float4 nt = T4[4 * (i0 + k)];
+                        if (!(dot(mk(nt.x, nt.y, nt.z), r.d) > 0.0f)) nib |= 1u << k;
+                    }
+                    m |= nib << i0;
+                }
+                if (n < 32) m &= (1u << n) - 1u;
+                const unsigned ib = (unsigned)(ign - c0);
+                if (ib < 32u) m &= ~(1u << ib);
+                if (!go) m = 0u;
+            } else {
 #pragma unroll kPathUnroll
-            for (int i = 0; i < n; i++) {
-                const float4 nt = T4[4 * i];
-                const bool ig = __float_as_int(nt.w) == ign;
-                const bool back = dot(mk(nt.x, nt.y, nt.z), r.d) > 0.0f;
-                if (COUNT && go) { ctr.nTriRef++; if (!ig) { if (back) ctr.nTriCulled++; else ctr.nTriFull++; } }
-                if (go && !ig && !back) m |= 1u << i;
+                for (int i = 0; i < n; i++) {
+                    const float4 nt = T4[4 * i];
+                    const bool ig = __float_as_int(nt.w) == ign;
+                    const bool back = dot(mk(nt.x, nt.y, nt.z), r.d) > 0.0f;
+                    if (COUNT && go) { ctr.nTriRef++; if (!ig) { if (back) ctr.nTriCulled++; else ctr.nTriFull++; } }
+                    if (go && !ig && !back) m |= 1u << i;
+                }
             }
             // pass 2: the full test (RayExtensions.cs:52-75), warp-uniform over the union of the lanes' survivors
             unsigned any = __reduce_or_sync(FULL, m);
@@ -193,20 +236,26 @@ __device__ __forceinline__ void pixelOf32(const DevFrame& F, unsigned q, int& x,
     }
 }
 
-// Level-0 ray of shard-local pixel / sample `idx` (RayTracer.Render, RayTracer.cs:410-421).
-__device__ __forceinline__ void primaryRay(const DevFrame& F, unsigned idx, V3& o, V3& d) {
+// Level-0 ray of shard-local pixel / sample `idx` (RayTracer.Render, RayTracer.cs:410-421).  Returns where the pixel's
+// colour goes (renderTargetData[y*W + x], :425; out[q] for a sample batch): the lane keeps that instead of `idx`, so the
+// index -> (x, y) division runs once per pixel.  xnart_capi.cu (usePath) keeps frames of 2^31 pixels or more off this kernel.
+__device__ __forceinline__ int primaryRay(const DevFrame& F, unsigned idx, V3& o, V3& d) {
     float sx, sy;
+    int at;
     if (F.samples) {   // GetColorForQuadrant's sub-pixel positions (RayTracer.cs:220-232)
         const float2 sp = F.samples[(unsigned long long)F.pixelBase + idx];
         sx = sp.x; sy = sp.y;
+        at = (int)((unsigned)F.pixelBase + idx);
     } else {
         int x, y;
         pixelOf32(F, (unsigned)F.pixelBase + idx, x, y);
         sx = (float)x; sy = (float)y;
+        at = y * F.vpW + x;
     }
     o = unproject(F, sx, sy, F.ndcZ[0]);
     const V3 farP = unproject(F, sx, sy, F.ndcZ[1]);
     d = normalize(sub(farP, o));
+    return at;
 }
 
 // One lane = one pixel's path; one iteration of the loop = ONE GetRayIntersection query per lane.  A lane is in
@@ -236,7 +285,7 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
     float4 recA[kPathLevels];   // (lightResult.xyz, 1 - Reflectiveness)
     float4 recB[kPathLevels];   // (surfaceColor.xyz, -)
 
-    int pix = -1;       // shard-local pixel this lane is working on, -1 = idle
+    int pix = -1;       // the pixel this lane is working on (its index in `out`), -1 = idle
     int level = 0;      // `iteration` of CastRay
     int q = -1;         // phase: -1 closest hit, >= 0 shadow query of light q
     // idle lanes carry a harmless ray so that the predicated arithmetic never takes a division slow path
@@ -273,7 +322,7 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
                 idle = __ballot_sync(FULL, pix < 0);
             }
             if (fresh) {
-                primaryRay(F, (unsigned)pix, ro, rd);
+                pix = primaryRay(F, (unsigned)pix, ro, rd);   // from here on: the pixel's position in `out`
                 level = 0; q = -1; ignM = -1; ignT = -1;
             }
             if (idle == FULL) break;   // nothing left in the frame and every lane has finished its path
@@ -337,9 +386,7 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
                 const V3 cv = mulv(lerp(unpackColor(col), mk(b.x, b.y, b.z), a.w), mk(a.x, a.y, a.z));
                 col = packColor(cv, F.semantics);
             }
-            int x, y;
-            pixelOf32(F, (unsigned)F.pixelBase + (unsigned)pix, x, y);
-            out[(size_t)y * (size_t)F.vpW + (size_t)x] = col;   // renderTargetData[y*W + x] (:425)
+            out[(unsigned)pix] = col;   // renderTargetData[y*W + x] (:425)
             pix = -1;
             ro = mk(0.0f, 0.0f, 0.0f); rd = mk(0.48f, 0.6f, 0.64f);
         }

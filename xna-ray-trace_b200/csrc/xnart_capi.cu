@@ -569,6 +569,11 @@ int32_t xnart_build_scene(XnartCtx* c, int32_t itemThreshold) {
             std::memcpy(P.rootBox, dm.rootBox, 24);
             P.obj = oi; P.mesh = mi; P.cls = dob.xformClass;
             P.first = firstOf[(size_t)mi]; P.count = dm.rootB; P.refBase = dm.rootA;
+            P.identity = 1;
+            for (int k = 0; k < P.count; k++) {
+                int id; std::memcpy(&id, &SS.tri[4 * (P.first + k)].w, sizeof id);
+                if (id != k) P.identity = 0;
+            }
             P.boxCoversRoot = 1;
             for (int a = 0; a < 3; a++)
                 if (!(dm.box[a] <= dm.rootBox[a] && dm.box[3 + a] >= dm.rootBox[3 + a])) P.boxCoversRoot = 0;
@@ -795,7 +800,9 @@ static int enqueueFrame(XnartCtx* c, DeviceState& d, const XnartFrame& f, uint32
     d.lastLights = F.nLights;
     d.progressEnqueued += (unsigned long long)localPixels;
     const bool mono = f.semantics == XNART_SEMANTICS_MONOGAME;   // compatibility mode: the generic level kernel, MonoGame slab form
-    if (!mono && usePath(c, d)) {
+    // the path kernel keeps a pixel's position in the frame as a 32-bit index (path.cu: primaryRay)
+    const bool fitsPath = devSamples ? nSamples <= 0x7fffffffLL : (long long)f.vpW * (long long)f.vpH <= 0x7fffffffLL;
+    if (!mono && fitsPath && usePath(c, d)) {
         if (localPixels > 0x7fffffffLL) return fail(c, XNART_ERR_UNSUPPORTED, "too many pixels in one shard");
         // no arena, no chunks: one persistent launch renders the shard (path.cu)
         F.tiled = (!devSamples && (f.vpW % 8 == 0) && (localPixels % (4LL * f.vpW) == 0)) ? 1 : 0;
