@@ -105,12 +105,11 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
         }
     }
     float bd = FLT_MAX;
-    out.obj = out.mesh = out.tri = -1; out.key = 0; out.u = out.v = 0.0f; out.d = 0.0f;
-    out.pos = mk(0.0f, 0.0f, 0.0f);
+    // `out` is written by the first accepted triangle and only read by the caller after a hit; `r` is written in the first
+    // iteration below (no class is -1): neither is initialised here — zeroing them cost 20 instructions per query
     if (!__any_sync(FULL, live)) return false;
     int cls = -1;
     RayPre r;
-    r.o = r.d = r.inv = mk(0.0f, 0.0f, 0.0f); r.par = r.oct = 0;
     bool rOk = false, rPar = false;
 #pragma unroll 1
     for (int p = 0; p < SS.nPairs; p++) {
@@ -139,7 +138,7 @@ __device__ __forceinline__ bool traceSmall(const SmallScene& SS, bool act, V3 ro
         go = slab6(P.rootBox, r, rPar, ct) && go;     // root of the MeshOctree (MeshOctree.cs:331)
         if (!__any_sync(FULL, go)) continue;
         const int ign = (ignM == P.mesh) ? ignT : -1;
-        V3 po = mk(0.0f, 0.0f, 0.0f);
+        V3 po;   // set with `improved`
         bool improved = false;
 #pragma unroll 1
         for (int c0 = 0; c0 < P.count; c0 += 32) {
