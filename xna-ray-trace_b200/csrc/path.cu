@@ -358,7 +358,7 @@ k_path(const __grid_constant__ SmallScene SS, DevScene S, const __grid_constant_
         } else {
             // opaque occluders only: amount is 1 or 0 (:487-501); :538-541
             const float amount = (hit && h.d < distToLight) ? 1.0f : 0.0f;
-            if (amount != 1.0f) lightResult = add(lightResult, mul(lightForFragment(lights[q], ro, N), 1.0f - amount));
+            if (amount != 1.0f) lightResult = add(lightResult, mul(lightForFragmentTo(lights[q], qd, N), 1.0f - amount));   // qd = Normalize(Position - ro)
             q++;
             shaded = q == F.nLights;
         }

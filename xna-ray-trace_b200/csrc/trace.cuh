@@ -719,13 +719,14 @@ __device__ __forceinline__ V3 lookupUV(const uint32_t* __restrict__ tex, int W, 
 // ---------------------------------------------------------------------------------------------
 // ILight.GetLightForFragment
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ V3 lightForFragment(const DevLight& L, V3 position, V3 normal) {
+// `toL`: Normalize(Position - position) of a spot light when the caller already has it (the shadow ray's direction,
+// shade.cuh: shadowDir — the same operations on the same operands).
+__device__ __forceinline__ V3 lightForFragmentTo(const DevLight& L, V3 toL, V3 normal) {
     if (L.kind == XNART_LIGHT_DIRECTIONAL) {  // DirectionalLight.cs:23-30 (uses +Direction)
         float sd = dot(mk(L.dx, L.dy, L.dz), normal);
         if (sd < 0.0f) sd = 0.0f;
         return mul(mul(mk(L.cr, L.cg, L.cb), sd), L.intensity);
     }
-    V3 toL = normalize(sub(mk(L.px, L.py, L.pz), position));
     float sd = dot(toL, normal);
     if (sd < 0.0f) return mk(0.0f, 0.0f, 0.0f);
     float ld = dot(neg(toL), mk(L.dx, L.dy, L.dz));
@@ -740,6 +741,11 @@ __device__ __forceinline__ V3 lightForFragment(const DevLight& L, V3 position, V
         return add(a, mk(1.0f * hl, 1.0f * hl, 1.0f * hl));
     }
     return mk(0.0f, 0.0f, 0.0f);
+}
+__device__ __forceinline__ V3 lightForFragment(const DevLight& L, V3 position, V3 normal) {
+    V3 toL = mk(0.0f, 0.0f, 0.0f);
+    if (L.kind != XNART_LIGHT_DIRECTIONAL) toL = normalize(sub(mk(L.px, L.py, L.pz), position));
+    return lightForFragmentTo(L, toL, normal);
 }
 
 }  // namespace xn
