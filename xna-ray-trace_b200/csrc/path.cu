@@ -62,7 +62,7 @@ __device__ __forceinline__ V3 transform43p(V3 p, const float* m) {
 // (trace.cuh) — the same operations in the same order, without the predicated parallel-axis code, which made up half
 // of the slab test's instructions (ncu, profiles/r02k: 55 warp instructions per box, 3.7 boxes per query).
 __device__ __forceinline__ bool slab6(const float* b, const RayPre& r, bool anyPar, float& t) {
-    if (anyPar) return slab(make_float3(b[0], b[1], b[2]), make_float3(b[3], b[4], b[5]), r, t);
+    if (anyPar) { float tExit; return slabGeneral(make_float3(b[0], b[1], b[2]), make_float3(b[3], b[4], b[5]), r, t, tExit); }
     float tmin = 0.0f, tmax = FLT_MAX;
     const float x1 = (b[0] - r.o.x) * r.inv.x, x2 = (b[3] - r.o.x) * r.inv.x;
     tmin = fmaxf(fminf(x1, x2), tmin); tmax = fminf(fmaxf(x1, x2), tmax);

@@ -68,6 +68,9 @@ __device__ __forceinline__ RayPre prepRay(V3 o, V3 d) {
     return r;
 }
 
+#ifndef XN_SLAB_FAST
+#define XN_SLAB_FAST 1
+#endif
 // One axis of the slab test.  Returns false when the parallel branch rejects.
 __device__ __forceinline__ bool slabAxis(float mn, float mx, float p, float inv, bool par, float& tmin, float& tmax) {
     if (par) {
@@ -88,7 +91,7 @@ __device__ __forceinline__ bool slabAxis(float mn, float mx, float p, float inv,
 
 // BoundingBox.Intersects(ref Ray, out float?) — XNA 4.0 form.  tmin only grows and tmax only
 // shrinks, so the framework's per-axis `if (tmin > tmax) return null` equals one test at the end.
-__device__ __forceinline__ bool slab2(float3 mn, float3 mx, const RayPre& r, float& t, float& tExit) {
+__device__ __forceinline__ bool slabGeneral(float3 mn, float3 mx, const RayPre& r, float& t, float& tExit) {
     float tmin = 0.0f, tmax = FLT_MAX;
     bool ok = slabAxis(mn.x, mx.x, r.o.x, r.inv.x, r.par & 1, tmin, tmax);
     ok = slabAxis(mn.y, mx.y, r.o.y, r.inv.y, r.par & 2, tmin, tmax) && ok;
@@ -96,6 +99,25 @@ __device__ __forceinline__ bool slab2(float3 mn, float3 mx, const RayPre& r, flo
     t = tmin;
     tExit = tmax;
     return ok && !(tmin > tmax);
+}
+__device__ __forceinline__ bool slab2(float3 mn, float3 mx, const RayPre& r, float& t, float& tExit) {
+#if XN_SLAB_FAST
+    if (r.par == 0) {
+        float tmin = 0.0f, tmax = FLT_MAX;
+        // no component below the 1e-6 threshold (almost every ray): the three non-parallel axes of slabAxis alone —
+        // the predicated containment code of the general form was half of the test's instructions (ncu, profiles/r02k)
+        const float x1 = (mn.x - r.o.x) * r.inv.x, x2 = (mx.x - r.o.x) * r.inv.x;
+        tmin = fmaxf(fminf(x1, x2), tmin); tmax = fminf(fmaxf(x1, x2), tmax);
+        const float y1 = (mn.y - r.o.y) * r.inv.y, y2 = (mx.y - r.o.y) * r.inv.y;
+        tmin = fmaxf(fminf(y1, y2), tmin); tmax = fminf(fmaxf(y1, y2), tmax);
+        const float z1 = (mn.z - r.o.z) * r.inv.z, z2 = (mx.z - r.o.z) * r.inv.z;
+        tmin = fmaxf(fminf(z1, z2), tmin); tmax = fminf(fmaxf(z1, z2), tmax);
+        t = tmin;
+        tExit = tmax;
+        return !(tmin > tmax);
+    }
+#endif
+    return slabGeneral(mn, mx, r, t, tExit);
 }
 __device__ __forceinline__ bool slab(float3 mn, float3 mx, const RayPre& r, float& t) {
     float tExit;
