@@ -850,3 +850,35 @@ def test_transparent_scene_arena_overflow_is_retried(X, oracle_mod):
     st.synchronize()
     assert np.array_equal(dev.cpu().numpy().view(np.uint32), want)
     x.close()
+
+
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_path_kernel_shortcuts_equal_oracle(X, oracle_mod, schedule):
+    """The exact shortcuts of k_path on the inputs that select each side of them: a camera INSIDE the
+    scene root's box (the root slab test is skipped for primary rays too) and one outside; an even-width top-down view
+    whose centre column has |d.x| < 1e-6 (the general slab form for those warps, the fast one for the others); an
+    axis-parallel directional light next to the spot light (every shadow ray of it has two parallel axes; black
+    chains fold 0 / 255f)."""
+    s = scenes.crate_scene()
+    s.lights.append(scenes.directional_light((0.0, -1.0, 0.0), color=(0.6, 0.7, 0.8), intensity=0.7))
+    s = s.finalize() if hasattr(s, "finalize") else s
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart()
+    x.set_option(records.OPT_TRAVERSAL, schedule)
+    scenes.upload(x, s)
+    cams = [scenes.CameraData((10.0, 15.0, 20.0), (0.0, 8.0, 0.0)),                      # inside the root box
+            scenes.CameraData((0.0, 55.0, 0.0), (0.0, 0.0, 0.0), up=(0.0, 0.0, -1.0)),   # straight down, inside
+            scenes.CameraData((0.0, 300.0, 0.0), (0.0, 0.0, 0.0), up=(0.0, 0.0, -1.0)),  # straight down, outside
+            scenes.CameraData((90.0, 20.0, -70.0), (0.0, 11.8, 0.0))]                     # outside, grazing the ground
+    for cam, wh in zip(cams, [(160, 120), (160, 120), (160, 120), (200, 96)]):
+        f = s.frame(*wh, camera=cam)
+        want = o.render_frame(f, n_threads=8)
+        got = x.render_frame(f)
+        assert len(np.unique(want)) > 50, "a frame without content tests nothing"
+        diff = int((want != got).sum())
+        assert diff == 0, "%d of %d pixels differ (camera %s)" % (diff, want.size, cam.position)
+        oc, xc = o.counters(), x.counters()
+        for k in ("raysPrimary", "raysShadow", "raysReflection", "hits"):
+            assert getattr(oc, k) == getattr(xc, k), k
+    x.close()
