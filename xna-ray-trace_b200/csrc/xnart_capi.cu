@@ -1101,6 +1101,8 @@ static int renderFrameDeviceBody(XnartCtx* c, const XnartFrame* frame, void* dev
     ProgressScope ps(c, (unsigned long long)localRowsOf(frame->vpH, si, sc, br) * (unsigned long long)frame->vpW);
     rc = enqueueAll();
     if (rc != XNART_OK) return rc;
+    if (!sub && d.countersHost && cudaMemcpyAsync(d.countersHost, d.counters, kCounterSnapBytes, cudaMemcpyDeviceToHost, st) == cudaSuccess)
+        d.countersPrefetched = true;   // read by collectCounters after the synchronisation below
     CU_TRY(c, cudaStreamSynchronize(st));
     c->last.msCopy = 0; c->last.msTotal = 0;
     rc = collectCounters(c);
