@@ -681,7 +681,7 @@ def flythrough_avi(x, scene, n_frames, world, rank, dev, torch, dist):
                     tmpdir = None
             fd, path = tempfile.mkstemp(suffix=".avi", prefix="xnart_fly_", dir=tmpdir or None)
             os.close(fd)
-            mgr = avi.AviManager(path, False, io_threads=4)
+            mgr = avi.AviManager(path, False, io_threads=8)
             sink = mgr.AddVideoStream(False, 30, 0, W, H, avi.PIXELFORMAT_24BPP_RGB)   # 30 fps as Game1.cs:198
         except Exception as e:
             err, sink = "cannot create the AVI file: %s" % e, None
