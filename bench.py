@@ -287,7 +287,11 @@ def main():
     # step is being rendered (XNART_BENCH_GATHER):
     #   "p2p"   every rank copies its half straight into a receive buffer of rank 0 (CUDA IPC handle from
     #           xnart_ipc_export, device-to-device xnart_copy_async on a copy stream: copy engines over NVLink, no
-    #           SMs); a one-element all-reduce ordered after the copy is the per-step completion signal.
+    #           SMs) and then, on the same stream, the step's number into its slot of a stamp array of rank 0 — the
+    #           completion signal, also moved by a copy engine.  A rank may reuse a ring half once its OWN copy of it
+    #           has finished (a local event); rank 0 checks the stamps when the timed region ends.  (A one-element
+    #           all-reduce per step was the signal before: its kernel had to find a free SM between persistent
+    #           k_path launches that fill the machine — 18.9 vs 17.6 ms per step at 8 GPUs.)
     #   "nccl"  one async dist.gather per step; its receive kernels on rank 0 share the SMs with the rendering.
     ring = torch.zeros((2, FPS, H, W), dtype=torch.int32, device=dev)
     half_bytes = FPS * H * W * 4
@@ -296,14 +300,18 @@ def main():
     gathered = [None, None]
     recv_ptr, remote_ptr = [None, None], [None, None]
     copy_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    done_ev = [None, None]          # p2p: this rank's copy of ring[half] (and its stamp) has finished
+    stamp_ptr = None                # p2p: world x int64 on rank 0, slot r = number of the last step rank r delivered
     if gather_mode == "p2p":
         box = [None]
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
             if rank == 0:
                 recv_ptr = [capi.alloc_device(local_rank, world * half_bytes) for _ in range(2)]
-                box[0] = [capi.ipc_export(local_rank, p) for p in recv_ptr]
+                stamp_ptr = capi.alloc_device(local_rank, 8 * world)
+                capi.copy_async(local_rank, stamp_ptr, torch.zeros(world, dtype=torch.int64, device=dev).data_ptr(), 8 * world, stream.cuda_stream)
+                torch.cuda.synchronize()
+                box[0] = [capi.ipc_export(local_rank, p) for p in recv_ptr] + [capi.ipc_export(local_rank, stamp_ptr)]
         except Exception as e:
             print("bench: CUDA IPC export failed (%s)" % e, file=sys.stderr)
             box[0] = None
@@ -312,7 +320,8 @@ def main():
             if box[0] is None:
                 raise RuntimeError("no handles")
             if rank != 0:
-                remote_ptr = [capi.ipc_open(local_rank, h) for h in box[0]]
+                remote_ptr = [capi.ipc_open(local_rank, h) for h in box[0][:2]]
+                stamp_ptr = capi.ipc_open(local_rank, box[0][2])
         except Exception as e:
             print("bench: CUDA IPC open failed on rank %d (%s)" % (rank, e), file=sys.stderr)
             ok.zero_()
@@ -327,7 +336,9 @@ def main():
     step_frames = [[scene.frame(W, H, camera=orbit_camera(scenes, (s * FPS + k) * world + rank)) for k in range(FPS)]
                    for s in range(warm + args.steps)]
 
-    def ship(half):
+    stamps = torch.arange(1, warm + args.steps + 2, dtype=torch.int64, device=dev)   # stamps[s] = s + 1: the source of the stamp copies
+
+    def ship(half, s):
         if world == 1:
             return
         if gather_mode == "nccl":
@@ -336,22 +347,29 @@ def main():
         copy_stream.wait_stream(stream)
         dst = (recv_ptr if rank == 0 else remote_ptr)[half] + rank * half_bytes
         capi.copy_async(local_rank, dst, ring[half].data_ptr(), half_bytes, copy_stream.cuda_stream)
-        with torch.cuda.stream(copy_stream):
-            pending[half] = dist.all_reduce(flag, async_op=True)   # done => every rank's half has landed
+        capi.copy_async(local_rank, stamp_ptr + 8 * rank, stamps[s].data_ptr(), 8, copy_stream.cuda_stream)   # after the frames, in stream order
+        done_ev[half] = torch.cuda.Event()
+        done_ev[half].record(copy_stream)
 
     def step(s):
         half = s & 1
         if pending[half] is not None:
             pending[half].wait()   # the render stream waits until this half's previous transfer has finished
             pending[half] = None
+        if done_ev[half] is not None:
+            stream.wait_event(done_ev[half])
+            done_ev[half] = None
         x.render_frames_device(step_frames[s], ring[half].data_ptr(), stream.cuda_stream)
-        ship(half)
+        ship(half, s)
 
     def drain():
         for b in range(2):
             if pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
+            if done_ev[b] is not None:
+                stream.wait_event(done_ev[b])
+                done_ev[b] = None
 
     def barrier():
         drain()
@@ -381,11 +399,14 @@ def main():
         if gather_mode == "p2p":
             g = torch.zeros((world, FPS, H, W), dtype=torch.int32, device=dev)
             capi.copy_async(local_rank, g.data_ptr(), recv_ptr[last], world * half_bytes, stream.cuda_stream)
+            got_stamps = torch.zeros(world, dtype=torch.int64, device=dev)
+            capi.copy_async(local_rank, got_stamps.data_ptr(), stamp_ptr, 8 * world, stream.cuda_stream)
             torch.cuda.synchronize()
+            stamps_ok = bool((got_stamps == warm + args.steps).all().item())   # every rank delivered its last step
         else:
             g = torch.stack(gathered[last])
         sums = [int(g[r, 0].to(torch.int64).bitwise_and(0xFFFFFF).sum().item()) for r in range(world)]
-        gather_ok = all(v > 0 for v in sums) and len(set(sums)) == world
+        gather_ok = all(v > 0 for v in sums) and len(set(sums)) == world and (gather_mode != "p2p" or stamps_ok)
         del g
     # the frames the timed region left behind (its last step) must be the frames an untimed render of that step gives
     last_half = (warm + args.steps - 1) & 1
@@ -587,7 +608,7 @@ def main():
             "config": cfg,
             "run": {"frames_per_step_per_gpu": FPS, "frames_in_flight": INFLIGHT,
                     "parallelism": ("frames sharded across GPUs (%d per GPU per step); every step's frames are shipped to rank 0 (%s) while the next step renders"
-                                    % (FPS, "device-to-device copies into an IPC-shared buffer of rank 0 + a 1-element all-reduce per step"
+                                    % (FPS, "device-to-device copies into an IPC-shared buffer of rank 0, each followed by a step stamp in rank 0's stamp array; no collective in the data path"
                                        if gather_mode == "p2p" else "async NCCL gather")) if world > 1 else "single GPU",
                     "l2": "each step writes %d MB of frames (ring of 2 steps) — larger than the 126 MB L2 — from %d different cameras; the "
                           "scene itself is 1.5 KB in the constant bank and cannot be made larger than a cache" % (half_bytes >> 20, ORBIT),
