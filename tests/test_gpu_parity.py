@@ -882,3 +882,26 @@ def test_path_kernel_shortcuts_equal_oracle(X, oracle_mod, schedule):
         for k in ("raysPrimary", "raysShadow", "raysReflection", "hits"):
             assert getattr(oc, k) == getattr(xc, k), k
     x.close()
+
+
+def test_crate_orbit_cameras_equal_oracle(X, oracle_mod):
+    """The bench's workload shape at a size the oracle renders in milliseconds: 24 cameras on the orbit of bench.py
+    (radius 72, height 35), every pixel of every frame against the oracle, through the batch call the bench times."""
+    import math
+    s = scenes.crate_scene()
+    o = oracle_mod.Oracle()
+    scenes.upload(o, s)
+    x = X.Xnart(frames_in_flight=2)
+    scenes.upload(x, s)
+    W, H = 480, 272
+    frames = []
+    for i in range(24):
+        rot = 2.0 * math.pi * i / 24
+        cam = scenes.CameraData((math.sin(rot) * 72.0, 35.0, math.cos(rot) * 72.0), (0.0, 11.8, 0.0))
+        frames.append(s.frame(W, H, camera=cam))
+    got = x.render_frames(frames)
+    for i, f in enumerate(frames):
+        want = o.render_frame(f, n_threads=8)
+        diff = int((want != got[i]).sum())
+        assert diff == 0, "camera %d: %d of %d pixels differ" % (i, diff, want.size)
+    x.close()
